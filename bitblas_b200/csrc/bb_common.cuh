@@ -1,0 +1,219 @@
+// bb_common.cuh -- shared host/device helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/bitblas_b200.h"
+
+namespace bb {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define BB_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      bb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 2;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define BB_LAUNCH_CHECK()                                                                    \
+  do {                                                                                       \
+    bb::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                 \
+      bb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 3;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+struct MatmulArgs {
+  bb_matmul_desc d;
+  const void* A;
+  const void* W;
+  const void* lut;
+  const void* scale;
+  const void* zeros;
+  const void* bias;
+  void* C;
+  int m;
+  void* workspace;
+  size_t workspace_bytes;
+  cudaStream_t stream;
+  int groups() const { return d.K / (d.group_size <= 0 ? d.K : d.group_size); }
+  int gsize() const { return d.group_size <= 0 ? d.K : d.group_size; }
+};
+
+int device_sm_count();
+
+// kernel family entry points (each returns 0 / error code; *_supported says whether the family covers it)
+bool generic_supported(const bb_matmul_desc& d);
+int launch_generic(const MatmulArgs& a);
+bool gemv_mma_supported(const bb_matmul_desc& d, int m);
+int launch_gemv_mma(const MatmulArgs& a);
+bool gemv_i8_supported(const bb_matmul_desc& d, int m);
+int launch_gemv_i8(const MatmulArgs& a);
+bool gemm_ts_supported(const bb_matmul_desc& d, int m);
+int launch_gemm_ts(const MatmulArgs& a);
+size_t gemm_ts_workspace_bytes(const bb_matmul_desc& d, int m);
+int gemm_ts_init(int device);
+
+// bit position of logical element `o` (0 .. 32/bits-1) inside its 32-bit storage word, for each weight
+// layout (restates bitblas/quantization/utils.py:73-110 + testing/cpp/lop3_type_conversion/fast_decoding.hpp:30-95,607-668)
+__host__ __device__ __forceinline__ int field_bitpos(int o, int bits, int layout) {
+  if (layout == BB_LAYOUT_COMPRESSED) return o * bits;
+  const int S = (layout == BB_LAYOUT_INTERLEAVED_8) ? 8 : 16;
+  const int G = 32 / S;
+  int pos = (o % G) * S + (o / G) * bits;
+  if (bits == 2 && S == 16) {
+    const int byte = pos >> 3;
+    if (byte == 1) pos += 8; else if (byte == 2) pos -= 8;
+  } else if (bits == 1 && S == 16) {
+    const int map[8] = {0, 2, 4, 6, 1, 3, 5, 7};
+    pos = map[pos >> 2] * 4 + (pos & 3);
+  } else if (bits == 1 && S == 8) {
+    const int map[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+    pos = map[pos >> 2] * 4 + (pos & 3);
+  }
+  return pos;
+}
+
+// ---- small device utilities -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t x, uint32_t mask, uint32_t orv) {
+  uint32_t r;
+  // (x & mask) | orv   -- immLut = (0xf0 & 0xcc) | 0xaa = 0xea
+  asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(r) : "r"(x), "r"(mask), "r"(orv));
+  return r;
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+template <typename T>
+struct TypeTraits;
+template <>
+struct TypeTraits<__half> {
+  static constexpr uint32_t kMagic = 0x64006400u;   // 1024.0 : (1024 + u) exact for u < 1024
+  static constexpr uint32_t kMagicHi = 0x64006400u; // for nibble at bit 4: 1024 + 16u
+  static constexpr int kMagicVal = 1024;
+  using T2 = __half2;
+  static __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_float(float v) { return __float2half_rn(v); }
+};
+template <>
+struct TypeTraits<__nv_bfloat16> {
+  static constexpr uint32_t kMagic = 0x43004300u;  // 128.0 : (128 + u) exact for u < 128
+  static constexpr int kMagicVal = 128;
+  using T2 = __nv_bfloat162;
+  static __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+__device__ __forceinline__ uint32_t b2_as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __nv_bfloat162 u32_as_b2(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+
+// packed 16-bit x2 arithmetic on raw registers, dispatched on element type
+template <typename T>
+__device__ __forceinline__ uint32_t sub2(uint32_t a, uint32_t b);
+template <>
+__device__ __forceinline__ uint32_t sub2<__half>(uint32_t a, uint32_t b) {
+  return h2_as_u32(__hsub2(u32_as_h2(a), u32_as_h2(b)));
+}
+template <>
+__device__ __forceinline__ uint32_t sub2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  return b2_as_u32(__hsub2(u32_as_b2(a), u32_as_b2(b)));
+}
+template <typename T>
+__device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b);
+template <>
+__device__ __forceinline__ uint32_t mul2<__half>(uint32_t a, uint32_t b) {
+  return h2_as_u32(__hmul2(u32_as_h2(a), u32_as_h2(b)));
+}
+template <>
+__device__ __forceinline__ uint32_t mul2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  return b2_as_u32(__hmul2(u32_as_b2(a), u32_as_b2(b)));
+}
+template <typename T>
+__device__ __forceinline__ uint32_t fma2(uint32_t a, uint32_t b, uint32_t c);
+template <>
+__device__ __forceinline__ uint32_t fma2<__half>(uint32_t a, uint32_t b, uint32_t c) {
+  return h2_as_u32(__hfma2(u32_as_h2(a), u32_as_h2(b), u32_as_h2(c)));
+}
+template <>
+__device__ __forceinline__ uint32_t fma2<__nv_bfloat16>(uint32_t a, uint32_t b, uint32_t c) {
+  return b2_as_u32(__hfma2(u32_as_b2(a), u32_as_b2(b), u32_as_b2(c)));
+}
+template <typename T>
+__device__ __forceinline__ uint32_t dup2(T v) {
+  uint16_t b = *reinterpret_cast<uint16_t*>(&v);
+  return (uint32_t(b) << 16) | b;
+}
+
+// ---- in-register decode of packed low-bit words -----------------------------------------------
+// 4-bit, 16-bit target.  Returns raw "magic + u" pairs (bias removed by the caller with one sub/fma).
+//   interleaved layout (quantization/utils.py:73-110): out[i] = (u[2i], u[2i+1])       i = 0..3
+//   compressed  layout:                                 out[i] = (u[i],  u[i+4])         i = 0..3
+template <typename T>
+__device__ __forceinline__ void decode_u4x8_raw(uint32_t w, uint32_t (&out)[4]) {
+  constexpr uint32_t M = TypeTraits<T>::kMagic;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = lop3_and_or(w >> (4 * i), 0x000f000fu, M);
+}
+// 2-bit, 16-bit target, interleaved layout: one 32-bit word = 16 values; out[i] = (u[2i], u[2i+1]) i = 0..7
+template <typename T>
+__device__ __forceinline__ void decode_u2x16_raw_interleaved(uint32_t w, uint32_t (&out)[8]) {
+  constexpr uint32_t M = TypeTraits<T>::kMagic;
+  uint32_t lo = __byte_perm(w, 0, 0x4140);  // [b0, 0, b1, 0]
+  uint32_t hi = __byte_perm(w, 0, 0x4342);  // [b2, 0, b3, 0]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out[i] = lop3_and_or(lo >> (2 * i), 0x00030003u, M);
+    out[4 + i] = lop3_and_or(hi >> (2 * i), 0x00030003u, M);
+  }
+}
+// 2-bit, 16-bit target, compressed layout: out[i] = (u[i], u[i+8]) i = 0..7
+template <typename T>
+__device__ __forceinline__ void decode_u2x16_raw_compressed(uint32_t w, uint32_t (&out)[8]) {
+  constexpr uint32_t M = TypeTraits<T>::kMagic;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = lop3_and_or(w >> (2 * i), 0x00030003u, M);
+}
+
+// 8-bit target.  interleaved-8 layout: out[i] = (u[4i..4i+3]) as 4 bytes.
+//   2-bit: 16 values / word, i = 0..3 ; 4-bit: 8 values / word, i = 0..1
+// `orv` is OR-ed in the same LOP3 (0 or 0x80808080 for the borrow-free signed trick).
+__device__ __forceinline__ void decode_u2x16_to_u8(uint32_t w, uint32_t orv, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = lop3_and_or(w >> (2 * i), 0x03030303u, orv);
+}
+__device__ __forceinline__ void decode_u4x8_to_u8(uint32_t w, uint32_t orv, uint32_t (&out)[2]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) out[i] = lop3_and_or(w >> (4 * i), 0x0f0f0f0fu, orv);
+}
+// bytes (u | 0x80) -> signed (u - zp) without inter-byte borrows: ((u|0x80) - zp) ^ 0x80
+__device__ __forceinline__ uint32_t bytes_sub_zp(uint32_t v_or80, uint32_t zp4) {
+  return (v_or80 - zp4) ^ 0x80808080u;
+}
+
+}  // namespace bb

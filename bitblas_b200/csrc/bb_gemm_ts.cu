@@ -1,0 +1,569 @@
+// bb_gemm_ts.cu -- the tensor-core path: tcgen05.mma with the dequantised weights as the TMEM ("TS") operand.
+//
+// Replaces the reference's generated mma.sync GEMM (bitblas/ops/general_matmul/tilelang/dequantize/
+// matmul_dequantize_mma.py:333-506: cp.async -> smem(int8) -> regs -> LOP3 decode -> smem(fp16) -> ldmatrix
+// -> mma.sync m16n8k16).  On B200 the decoded weights never touch shared memory:
+//
+//     C^T[n, m] = sum_k  Wdeq[n, k] * A[m, k]            (the operands are swapped: W is the MMA "A"/M side)
+//
+//   TMA warp      : per k-block, one 2-D tile of activations A[BM x 64] (fp16/bf16; 128 int8) into 128B-swizzled
+//                   shared memory (the MMA "B"/N operand, K-major) and one tile of PACKED weights
+//                   W[128 rows x 32 B] (4-bit) -- 8x fewer bytes than a dequantised tile;
+//   dequant warps : 8 warps, thread <-> weight row (= TMEM lane).  ld.shared 16 B -> LOP3 decode + (w-z)*s
+//                   in registers -> tcgen05.st into a ring of TMEM operand slots (32 columns per k-block);
+//   MMA warp      : one elected thread issues tcgen05.mma.kind::f16 (or kind::i8) M=128, N=BM, K=16 (32),
+//                   A operand from TMEM, B operand from the swizzled smem descriptor, fp32 (s32) accumulator
+//                   in TMEM; tcgen05.commit releases the smem stage and the TMEM slot through mbarriers;
+//   epilogue      : the dequant warps read the accumulator with tcgen05.ld, cast, add bias, store C[m, n].
+//
+// Shared-memory traffic per k-block is therefore A-tile (TMA write + MMA read) + 4 KB packed W, instead of
+// also writing and re-reading a 16-32 KB dequantised W tile -- the difference between fitting and not fitting
+// the 128 B/clk/SM shared-memory budget at full tensor rate.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "bb_common.cuh"
+
+namespace bb {
+
+namespace {
+
+constexpr int TS_ROWS = 128;    // weight rows per CTA = MMA M
+constexpr int DQ_WARPS = 8;
+constexpr int TS_THREADS = (2 + DQ_WARPS) * 32;
+constexpr int TA_SLOTS = 4;     // TMEM operand slots (k-blocks the dequant warps may run ahead)
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+template <bool INT8>
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (INT8) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory operand descriptor (rows of 128 B, 8-row swizzle atoms = 1024 B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= uint64_t(0) << 16;                      // leading byte offset: unused for swizzled K-major
+  d |= uint64_t(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+  d |= uint64_t(1) << 46;                      // descriptor version (sm_100)
+  d |= uint64_t(2) << 61;                      // SWIZZLE_128B
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TsParams {
+  const void* scale;
+  const void* zeros;
+  const void* bias;
+  void* C;
+  int M, N, K;
+  int g, G;
+  int mode;       // 0 none, 1 scale, 2 original, 3 rescale, 4 quantized
+  int zp_const;
+  int out_dtype;
+  int a_dtype;
+  int m_tiles;
+};
+
+template <typename T>
+struct ElemInfo {
+  static constexpr bool kInt8 = false;
+  static constexpr int kKB = 64;  // elements per 128-byte swizzle row
+  static constexpr int kUmmaK = 16;
+};
+template <>
+struct ElemInfo<int8_t> {
+  static constexpr bool kInt8 = true;
+  static constexpr int kKB = 128;
+  static constexpr int kUmmaK = 32;
+};
+
+template <int BM>
+struct TsTmem {
+  static constexpr int kAcol0 = BM < 32 ? 32 : BM;
+  static constexpr int kNeed = kAcol0 + TA_SLOTS * 32;
+  static constexpr int kCols = kNeed <= 64 ? 64 : (kNeed <= 128 ? 128 : (kNeed <= 256 ? 256 : 512));
+};
+
+template <typename T, int BITS, int BM>
+struct TsSmem {
+  static constexpr int kPRB = ElemInfo<T>::kKB * BITS / 8;  // packed bytes per row per k-block
+  static constexpr int kActBytes = BM * 128;
+  static constexpr int kWBytes = TS_ROWS * kPRB;
+  static constexpr int kStageBytes = kActBytes + kWBytes;
+  static constexpr int kStagesRaw = (220 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+// decode `PRB/2` packed bytes (this thread's half of the k-block) into 16 registers of natural-k-order
+// operand data.  16-bit targets.
+template <typename T, int BITS, int MODE>
+__device__ __forceinline__ void dequant_half_row(const uint8_t* src, uint32_t (&out)[16], uint32_t mz, uint32_t z2,
+                                                 uint32_t s2, uint32_t negz2) {
+  auto fin = [&](uint32_t x) -> uint32_t {
+    uint32_t t = sub2<T>(x, mz);
+    if constexpr (MODE == 0) return t;
+    if constexpr (MODE == 1 || MODE == 4) return mul2<T>(t, s2);
+    if constexpr (MODE == 2) return mul2<T>(sub2<T>(t, z2), s2);
+    if constexpr (MODE == 3) return fma2<T>(t, s2, negz2);
+    return t;
+  };
+  if constexpr (BITS == 4) {
+    const uint4 pk = *reinterpret_cast<const uint4*>(src);
+    const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t h[4];
+      decode_u4x8_raw<T>(w[i], h);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[4 * i + j] = fin(h[j]);
+    }
+  } else {
+    const uint2 pk = *reinterpret_cast<const uint2*>(src);
+    const uint32_t w[2] = {pk.x, pk.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint32_t h[8];
+      decode_u2x16_raw_interleaved<T>(w[i], h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[8 * i + j] = fin(h[j]);
+    }
+  }
+}
+
+template <int BITS>
+__device__ __forceinline__ void dequant_half_row_i8(const uint8_t* src, uint32_t (&out)[16], uint32_t zp4) {
+  if constexpr (BITS == 2) {
+    const uint4 pk = *reinterpret_cast<const uint4*>(src);
+    const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t h[4];
+      decode_u2x16_to_u8(w[i], zp4 ? 0x80808080u : 0u, h);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[4 * i + j] = zp4 ? bytes_sub_zp(h[j], zp4) : h[j];
+    }
+  } else {
+    const uint4 p0 = *reinterpret_cast<const uint4*>(src);
+    const uint4 p1 = *reinterpret_cast<const uint4*>(src + 16);
+    const uint32_t w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t h[2];
+      decode_u4x8_to_u8(w[i], zp4 ? 0x80808080u : 0u, h);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) out[2 * i + j] = zp4 ? bytes_sub_zp(h[j], zp4) : h[j];
+    }
+  }
+}
+
+template <typename T, int BITS, int BM>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TsParams p) {
+  using SM = TsSmem<T, BITS, BM>;
+  using EI = ElemInfo<T>;
+  constexpr int S = SM::kStages;
+  constexpr int KB = EI::kKB;
+  constexpr int PRB = SM::kPRB;
+  constexpr bool INT8 = EI::kInt8;
+  constexpr int ACOL0 = TsTmem<BM>::kAcol0;
+  constexpr int NCOLS = TsTmem<BM>::kCols;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + S * SM::kActBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * SM::kStageBytes);
+  uint64_t* full = bars;                 // [S]   TMA -> dequant + MMA
+  uint64_t* empty = bars + S;            // [S]   MMA commit -> TMA
+  uint64_t* a_ready = bars + 2 * S;      // [TA]  dequant -> MMA
+  uint64_t* a_free = a_ready + TA_SLOTS; // [TA]  MMA commit -> dequant
+  uint64_t* acc_full = a_free + TA_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x % p.m_tiles;
+  const int n_tile = blockIdx.x / p.m_tiles;
+  const int m0 = m_tile * BM, n0 = n_tile * TS_ROWS;
+  const int num_kb = p.K / KB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < TA_SLOTS; ++i) { mbar_init(&a_ready[i], DQ_WARPS); mbar_init(&a_free[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<NCOLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S;
+        if (kb >= S) mbar_wait(&empty[s], ((kb / S) - 1) & 1);
+        mbar_arrive_expect_tx(&full[s], SM::kStageBytes);
+        tma_load_2d(sA + s * SM::kActBytes, &tmA, kb * KB, m0, &full[s]);
+        tma_load_2d(sW + s * SM::kWBytes, &tmW, kb * PRB, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t idesc;
+      if constexpr (INT8) {
+        const uint32_t a_signed = p.zp_const ? 1u : 0u;
+        idesc = (2u << 4) | (a_signed << 7) | (1u << 10) | (uint32_t(BM >> 3) << 17) | (uint32_t(TS_ROWS >> 4) << 24);
+      } else {
+        const uint32_t f = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+        idesc = (1u << 4) | (f << 7) | (f << 10) | (uint32_t(BM >> 3) << 17) | (uint32_t(TS_ROWS >> 4) << 24);
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S, t = kb % TA_SLOTS;
+        mbar_wait(&full[s], (kb / S) & 1);
+        mbar_wait(&a_ready[t], (kb / TA_SLOTS) & 1);
+        tc_fence_after();
+        const uint64_t bdesc = make_sw128_desc(smem_u32(sA + s * SM::kActBytes));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          tc_mma_ts<INT8>(tmem_base, tmem_base + ACOL0 + t * 32 + kk * 8, bdesc + uint64_t(kk * 2), idesc,
+                          (kb > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty[s]);
+        tc_commit(&a_free[t]);
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // ===== dequant warps (then epilogue) =====
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may touch
+    const int half = (warp - 2) >> 2;       // which half of the k-block's columns
+    const int row = quad * 32 + lane;       // weight row inside the tile == TMEM lane
+    const int n = n0 + row;
+    const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
+    constexpr uint32_t MAGIC = INT8 ? 0u : TypeTraits<typename std::conditional<INT8, __half, T>::type>::kMagic;
+    using TF = typename std::conditional<INT8, __half, T>::type;  // float-ish type for the 16-bit path
+
+    uint32_t mz = MAGIC + uint32_t(p.zp_const) * 0x00010001u, z2 = 0, s2 = 0, negz2 = 0;
+    int cur_g = -1;
+    const int kb_per_g = p.g / KB;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % S, t = kb % TA_SLOTS;
+      if constexpr (!INT8) {
+        const int gi = kb / kb_per_g;
+        if (gi != cur_g && p.mode != 0) {
+          cur_g = gi;
+          const TF sv = reinterpret_cast<const TF*>(p.scale)[size_t(n) * p.G + gi];
+          s2 = dup2<TF>(sv);
+          if (p.mode == 2 || p.mode == 3) {
+            TF zv = reinterpret_cast<const TF*>(p.zeros)[size_t(n) * p.G + gi];
+            z2 = dup2<TF>(zv);
+            negz2 = z2 ^ 0x80008000u;
+          } else if (p.mode == 4) {
+            const uint8_t* qz = reinterpret_cast<const uint8_t*>(p.zeros) + size_t(gi) * (size_t(p.N) * BITS / 8);
+            constexpr int EPB = 8 / BITS;
+            const uint32_t zq = (qz[n / EPB] >> (BITS * (n % EPB))) & ((1u << BITS) - 1u);
+            mz = MAGIC + zq * 0x00010001u;
+          }
+        }
+      }
+      mbar_wait(&full[s], (kb / S) & 1);
+      if (kb >= TA_SLOTS) {
+        mbar_wait(&a_free[t], ((kb / TA_SLOTS) - 1) & 1);
+        tc_fence_after();
+      }
+      const uint8_t* src = sW + s * SM::kWBytes + row * PRB + half * (PRB / 2);
+      uint32_t regs[16];
+      if constexpr (INT8) {
+        dequant_half_row_i8<BITS>(src, regs, uint32_t(p.zp_const) * 0x01010101u);
+      } else {
+        switch (p.mode) {
+          case 0: dequant_half_row<TF, BITS, 0>(src, regs, mz, z2, s2, negz2); break;
+          case 1: dequant_half_row<TF, BITS, 1>(src, regs, mz, z2, s2, negz2); break;
+          case 2: dequant_half_row<TF, BITS, 2>(src, regs, mz, z2, s2, negz2); break;
+          case 3: dequant_half_row<TF, BITS, 3>(src, regs, mz, z2, s2, negz2); break;
+          default: dequant_half_row<TF, BITS, 4>(src, regs, mz, z2, s2, negz2); break;
+        }
+      }
+      tmem_st_x16(lane_addr + ACOL0 + t * 32 + half * 16, regs);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[t]);
+    }
+
+    // ----- epilogue: accumulator[lane = n, column = m] -> C[m, n] -----
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    constexpr int CPH = BM / 2;                  // columns per half
+    constexpr int CH = CPH < 16 ? CPH : 16;      // columns per tcgen05.ld (x16)
+    static_assert(CPH % CH == 0 && CH == 16, "BM must be >= 32");
+    float bias_f = 0.f;
+    if (p.bias) {
+      if (p.a_dtype == BB_F16) bias_f = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+      else if (p.a_dtype == BB_BF16) bias_f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+      else bias_f = float(reinterpret_cast<const int8_t*>(p.bias)[n]);
+    }
+    for (int c0 = half * CPH; c0 < (half + 1) * CPH; c0 += CH) {
+      if (m0 + c0 >= p.M) break;  // warp-uniform
+      uint32_t v[16];
+      tmem_ld_x16(lane_addr + c0, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int m = m0 + c0 + c;
+        if (m >= p.M) break;
+        const size_t o = size_t(m) * p.N + n;
+        if constexpr (INT8) {
+          const int acc = int(v[c]);
+          const int b = int(bias_f);
+          switch (p.out_dtype) {
+            case BB_I32: reinterpret_cast<int*>(p.C)[o] = acc + b; break;
+            case BB_I8: reinterpret_cast<int8_t*>(p.C)[o] = int8_t(int8_t(acc) + b); break;
+            case BB_F32: reinterpret_cast<float*>(p.C)[o] = float(acc) + float(b); break;
+            case BB_F16: reinterpret_cast<__half*>(p.C)[o] = __hadd(__int2half_rn(acc), __int2half_rn(b)); break;
+            default: reinterpret_cast<__nv_bfloat16*>(p.C)[o] = __hadd(__int2bfloat16_rn(acc), __int2bfloat16_rn(b));
+          }
+        } else {
+          const float acc = __uint_as_float(v[c]);
+          if (p.out_dtype == BB_F16) {
+            __half h = __float2half_rn(acc);
+            if (p.bias) h = __hadd(h, __float2half_rn(bias_f));
+            reinterpret_cast<__half*>(p.C)[o] = h;
+          } else if (p.out_dtype == BB_BF16) {
+            __nv_bfloat16 h = __float2bfloat16_rn(acc);
+            if (p.bias) h = __hadd(h, __float2bfloat16_rn(bias_f));
+            reinterpret_cast<__nv_bfloat16*>(p.C)[o] = h;
+          } else {
+            reinterpret_cast<float*>(p.C)[o] = acc + (p.bias ? bias_f : 0.f);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<NCOLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+EncodeTiledFn get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  return g_encode;
+}
+
+int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 4; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", int(r)); return 4; }
+  return 0;
+}
+
+template <typename T, int BITS, int BM>
+int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
+  using SM = TsSmem<T, BITS, BM>;
+  using EI = ElemInfo<T>;
+  auto kernel = gemm_ts_kernel<T, BITS, BM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_set = true;
+  }
+  TsParams p = p0;
+  p.m_tiles = (a.m + BM - 1) / BM;
+  CUtensorMap tmA, tmW;
+  const CUtensorMapDataType adt = EI::kInt8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                            : (std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                               : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  int rc = make_map_2d(&tmA, adt, a.A, uint64_t(a.d.K), uint64_t(a.m), uint64_t(a.d.K) * sizeof(T), EI::kKB, BM,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const uint64_t wrow = uint64_t(a.d.K) * BITS / 8;
+  rc = make_map_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, wrow, uint64_t(a.d.N), wrow, SM::kPRB, TS_ROWS,
+                   CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
+  const int grid = p.m_tiles * (a.d.N / TS_ROWS);
+  kernel<<<grid, TS_THREADS, SM::kTotal, a.stream>>>(tmA, tmW, p);
+  BB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int BITS>
+int launch_ts_bm(const MatmulArgs& a, const TsParams& p) {
+  if (a.m <= 32) return launch_ts_inst<T, BITS, 32>(a, p);
+  if (a.m <= 64) return launch_ts_inst<T, BITS, 64>(a, p);
+  if (a.m <= 128) return launch_ts_inst<T, BITS, 128>(a, p);
+  return launch_ts_inst<T, BITS, 256>(a, p);
+}
+
+}  // namespace
+
+bool gemm_ts_supported(const bb_matmul_desc& d, int m) {
+  if (m < 1) return false;
+  if (d.w_fmt != BB_W_UINT && d.w_fmt != BB_W_INT) return false;
+  if (d.w_bits != 4 && d.w_bits != 2) return false;
+  if (d.N % TS_ROWS) return false;
+  const int g = d.group_size <= 0 ? d.K : d.group_size;
+  if (d.a_dtype == BB_I8) {
+    if (d.accum_dtype != BB_I32 || d.w_layout != BB_LAYOUT_INTERLEAVED_8) return false;
+    if (d.with_scaling || d.with_zeros) return false;
+    if (d.K % 128) return false;
+    return true;
+  }
+  if (d.a_dtype != BB_F16 && d.a_dtype != BB_BF16) return false;
+  if (d.w_layout != BB_LAYOUT_INTERLEAVED_16) return false;
+  if (d.K % 64 || g % 64 || d.K % g) return false;
+  if (d.with_zeros && !d.with_scaling) return false;
+  if (d.w_fmt == BB_W_INT && d.with_zeros) return false;
+  if (d.out_dtype != BB_F16 && d.out_dtype != BB_BF16 && d.out_dtype != BB_F32) return false;
+  if (d.with_zeros && d.zeros_mode == BB_ZEROS_QUANTIZED && (d.N * d.w_bits) % 8) return false;
+  return true;
+}
+
+size_t gemm_ts_workspace_bytes(const bb_matmul_desc&, int) { return 0; }
+
+int gemm_ts_init(int) { return get_encode() ? 0 : 0; }
+
+int launch_gemm_ts(const MatmulArgs& a) {
+  const bb_matmul_desc& d = a.d;
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15)) {
+    set_error("gemm_ts: A and W must be 16-byte aligned");
+    return 5;
+  }
+  TsParams p;
+  p.scale = d.with_scaling ? a.scale : nullptr;
+  p.zeros = d.with_zeros ? a.zeros : nullptr;
+  p.bias = d.with_bias ? a.bias : nullptr;
+  p.C = a.C; p.M = a.m; p.N = d.N; p.K = d.K; p.g = a.gsize(); p.G = a.groups();
+  p.mode = !d.with_scaling ? 0 : (!d.with_zeros ? 1 : 2 + d.zeros_mode);
+  p.zp_const = d.w_fmt == BB_W_INT ? (1 << (d.w_bits - 1)) : 0;
+  p.out_dtype = d.out_dtype; p.a_dtype = d.a_dtype; p.m_tiles = 1;
+  if (d.a_dtype == BB_I8) return d.w_bits == 4 ? launch_ts_bm<int8_t, 4>(a, p) : launch_ts_bm<int8_t, 2>(a, p);
+  if (d.a_dtype == BB_F16) return d.w_bits == 4 ? launch_ts_bm<__half, 4>(a, p) : launch_ts_bm<__half, 2>(a, p);
+  return d.w_bits == 4 ? launch_ts_bm<__nv_bfloat16, 4>(a, p) : launch_ts_bm<__nv_bfloat16, 2>(a, p);
+}
+
+}  // namespace bb

@@ -1,0 +1,152 @@
+/*
+ * bitblas_b200.h -- C ABI of the B200-native low-bit-weight matmul library.
+ *
+ * This is the drop-in boundary for the ONE hot path of microsoft/BitBLAS: the dequantize-matmul behind
+ * bitblas.Matmul / bitblas.Linear.  In the reference every operator instance owns a generated .so that
+ * exports
+ *     extern "C" void init();
+ *     extern "C" void call(<T>* A, int8_t* B, [half* LUT], [half* Scale], [int8_t* Qzeros | half* Zeros],
+ *                          [half* Bias], <T>* C, [int m], cudaStream_t stream);
+ * (reference: bitblas/builder/wrapper/base.py:5-19, bitblas/builder/wrapper/tl.py:90-166,278-300; called
+ * from bitblas/ops/operator.py:458-463 and bitblas/module/__init__.py:287 via ctypes).
+ *
+ * Here ONE prebuilt library serves every MatmulConfig: the config travels in a POD descriptor and the
+ * entry points below replace init()/call().  Plain pointers and sizes only -- no torch types.  All device
+ * buffers are caller-owned; the library never allocates, frees or synchronises inside bb_matmul, so the call
+ * is CUDA-graph capturable.  Every function returns 0 on success; on failure a non-zero code is returned and
+ * bb_last_error() describes it (the reference returns void and swallows errors, operator.py:200-214).
+ */
+#ifndef BITBLAS_B200_H_
+#define BITBLAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_VERSION 100 /* 0.1.0 */
+
+/* element types of A / accumulator / output (MatmulConfig.A_dtype, accum_dtype, out_dtype:
+ * bitblas/ops/general_matmul/__init__.py:63-67) */
+typedef enum bb_dtype {
+  BB_F16 = 0,
+  BB_BF16 = 1,
+  BB_F32 = 2,
+  BB_I8 = 3,
+  BB_I32 = 4
+} bb_dtype;
+
+/* weight source formats (Matmul.BITBLAS_TRICK_DTYPE_MAP, general_matmul/__init__.py:324-345) */
+typedef enum bb_wfmt {
+  BB_W_UINT = 0,    /* "uint"    : u                               (quantization.py:200-208) */
+  BB_W_INT = 1,     /* "int"     : u - 2^(bits-1); 1-bit: 2u-1     (quantization.py:185-194, lop3.py:723-727) */
+  BB_W_NF = 2,      /* "nf"      : LUT[u]                          (matmul_dequantize_impl.py:424-430) */
+  BB_W_FP4 = 3,     /* "fp"      : sign + 3-bit exponent 2^(e-7)   (quantization.py:141-156) */
+  BB_W_FP8_E4M3 = 4,/* "fp_e4m3" : bit trick                       (quantization.py:169-176) */
+  BB_W_FP8_E5M2 = 5 /* "fp_e5m2" : reinterpret<<8                  (quantization.py:179-182) */
+} bb_wfmt;
+
+/* MatmulConfig.zeros_mode (general_matmul/__init__.py:73-78) */
+typedef enum bb_zeros_mode {
+  BB_ZEROS_ORIGINAL = 0,  /* (w - Z[n,k/g]) * S[n,k/g]   ; Z is A_dtype [N, K/g]            */
+  BB_ZEROS_RESCALE = 1,   /*  w * S[n,k/g] - Z[n,k/g]    ; Z is A_dtype [N, K/g]            */
+  BB_ZEROS_QUANTIZED = 2  /* (u - QZ[k/g,n]) * S[n,k/g]  ; QZ is `bits`-packed int8 [K/g, N*bits/8] */
+} bb_zeros_mode;
+
+/* weight storage layout of W[N, K*bits/8] int8 (general_matmul/__init__.py:557-565) */
+typedef enum bb_wlayout {
+  BB_LAYOUT_COMPRESSED = 0,      /* general_compress only            (quantization/utils.py:54-69)   */
+  BB_LAYOUT_INTERLEAVED_16 = 1,  /* + LOP3 interleave, 16-bit target (quantization/utils.py:73-110)  */
+  BB_LAYOUT_INTERLEAVED_8 = 2    /* + LOP3 interleave,  8-bit target (A_dtype == int8)               */
+} bb_wlayout;
+
+/* One matmul problem family: C[m, N] = A[m, K] x dequant(W[N, K])^T (+ bias).  Mirrors the fields of
+ * MatmulConfig that reach the kernel (general_matmul/__init__.py:58-95); `layout` is always "nt"
+ * (tirscript/matmul_dequantize_impl.py:912-915). */
+typedef struct bb_matmul_desc {
+  int32_t N;
+  int32_t K;
+  int32_t a_dtype;      /* bb_dtype: BB_F16 | BB_BF16 | BB_I8                         */
+  int32_t w_fmt;        /* bb_wfmt                                                    */
+  int32_t w_bits;       /* 1 | 2 | 4 | 8                                              */
+  int32_t accum_dtype;  /* bb_dtype: float accumulate is done in fp32; BB_I32 is exact */
+  int32_t out_dtype;    /* bb_dtype of C                                              */
+  int32_t group_size;   /* -1 (== K) or a divisor of K                                */
+  int32_t with_scaling; /* Scale[N, K/g] in A_dtype                                   */
+  int32_t with_zeros;
+  int32_t zeros_mode;   /* bb_zeros_mode                                              */
+  int32_t with_bias;    /* Bias[N] in out_dtype-compatible A_dtype                    */
+  int32_t w_layout;     /* bb_wlayout                                                 */
+  int32_t reserved[3];  /* must be 0                                                  */
+} bb_matmul_desc;
+
+/* kernel families the dispatcher can choose (introspection / tests) */
+typedef enum bb_kernel_id {
+  BB_KERNEL_AUTO = 0,
+  BB_KERNEL_GENERIC = 1,   /* SIMT, every config (spec-order arithmetic)                     */
+  BB_KERNEL_GEMV_MMA = 2,  /* m <= 32, fp16/bf16 A, 4/2-bit W: warp-level mma.sync streaming  */
+  BB_KERNEL_GEMV_I8 = 3,   /* m <= 32, int8 A, 4/2-bit W: IMMA streaming, int32 exact         */
+  BB_KERNEL_GEMM_TS = 4,   /* tcgen05 (W dequantised into TMEM as the MMA A operand) + TMA    */
+  BB_KERNEL_GEMM_TS_I8 = 5 /* tcgen05 kind::i8 variant                                        */
+} bb_kernel_id;
+
+/* replaces `init()` (builder/wrapper/base.py:5-13): one-time per-device setup (opt-in shared memory
+ * sizes, driver entry points).  Idempotent and thread-safe. */
+int bb_init(int device);
+
+/* replaces `call(...)` (builder/wrapper/base.py:15-19).  Pointer order follows the reference's
+ * A, B, [LUT], [Scale], [Zeros|Qzeros], [Bias], C, m, stream; absent operands are NULL.
+ * `m` = product of A's leading dims (general_matmul/__init__.py:746-748); m == 0 returns immediately
+ * (wrapper/tl.py:156-157).  `workspace` may be NULL unless bb_workspace_bytes() > 0.
+ * Asynchronous on `stream` (a cudaStream_t). */
+int bb_matmul(const bb_matmul_desc* desc, const void* A, const void* W, const void* lut, const void* scale,
+              const void* zeros, const void* bias, void* C, int m, void* workspace, size_t workspace_bytes,
+              void* stream);
+
+/* scratch (fp32 split-K partials) the chosen kernel needs for this (desc, m); 0 for most configs. */
+size_t bb_workspace_bytes(const bb_matmul_desc* desc, int m);
+
+/* which kernel family bb_matmul would run for (desc, m) -- bb_kernel_id; <0 on invalid desc. */
+int bb_select_kernel(const bb_matmul_desc* desc, int m);
+const char* bb_kernel_name(int kernel_id);
+/* testing hook: force a kernel family (BB_KERNEL_AUTO restores dispatch). Returns previous value. */
+int bb_set_kernel_override(int kernel_id);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches counter). */
+uint64_t bb_launch_count(void);
+
+const char* bb_last_error(void);
+int bb_version(void);
+
+/* ---- weight pre-processing (replaces the TVM-LLVM CPU ops QuantCompress / LOP3Permutate,
+ * bitblas/ops/quant_compress/quant_compress_impl.py:22-30, bitblas/ops/lop3_permutate/lop3_permutate_impl.py:27-34,
+ * chained by OPExecutorCPU, bitblas/ops/operator.py:529-556) ---- */
+
+/* host: in[rows, cols] one value per int8 -> out[rows, cols*bits/8] */
+int bb_compress_host(const int8_t* in, int8_t* out, int64_t rows, int64_t cols, int bits);
+/* host: per-int32-word LOP3 interleave; target_bits = 16 (f16/bf16 A) or 8 (int8 A) */
+int bb_interleave_host(const int8_t* in, int8_t* out, int64_t nbytes, int bits, int target_bits);
+/* device: fused compress (+ interleave if target_bits != 0) of w[rows, cols] int8 -> out[rows, cols*bits/8] */
+int bb_transform_weight_device(const int8_t* w, int8_t* out, int64_t rows, int64_t cols, int bits,
+                               int target_bits, void* stream);
+/* device: GPTQ ingest (bitblas/module/__init__.py:24-74,315-363).  qweight_gptq is int32 [K*bits/32, N]
+ * (GPTQ layout); writes BitBLAS layout out[N, K*bits/8] (compressed + optional interleave). */
+int bb_repack_gptq_qweight_device(const int32_t* qweight_gptq, int8_t* out, int64_t K, int64_t N, int bits,
+                                  int target_bits, void* stream);
+/* device: GPTQ qzeros int32 [K/g, N*bits/32] -> unpacked (+1 unless v2, & mask) transposed int8 [N, K/g]
+ * as A_dtype-typed `zeros_out` (mode original: value; rescale: value*scale) or re-packed [K/g, N*bits/8]
+ * (mode quantized).  scales is [N, K/g] in a_dtype (already transposed). */
+int bb_repack_gptq_qzeros_device(const int32_t* qzeros_gptq, const void* scales, void* zeros_out, int64_t groups,
+                                 int64_t N, int bits, int zeros_mode, int a_dtype, int v2, void* stream);
+
+/* ---- test hook: run the library's own in-register decode over an array of packed words (device ptrs).
+ * kind: 0 = to f16 (8 values / group), 1 = to bf16, 2 = to int8 (16 values / group).  Used by the GPU KATs
+ * that compare against the reference's device decode functions (oracle/ref_shim.cu). ---- */
+int bb_debug_decode(int kind, int bits, int is_signed, int w_layout, const void* in, void* out, int ngroups,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BITBLAS_B200_H_ */

@@ -1,0 +1,226 @@
+"""GPU parity: every kernel family, through the C ABI (Matmul.forward -> bb_matmul), against the CPU oracle on
+the same seeded inputs.  Bit-exact for INT accumulate, <= 1e-2 relative for FP accumulate (north_star)."""
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(case, expect_kernel=None):
+    op = H.product_operator(case)
+    if expect_kernel is not None:
+        assert op.kernel_for(case["M"]) == expect_kernel, (op.kernel_for(case["M"]), expect_kernel)
+    got = H.run_product(op, case)
+    ref = H.oracle_output(case, fast_decoding=bool(op.fast_decoding))
+    return op, got, ref
+
+
+GEMV_CASES = [
+    # reference GEMV cases (test_general_matmul_ops_backend_tl.py:327-334) at a 128-aligned size
+    dict(M=1, N=256, K=256, W_dtype="uint4"),
+    dict(M=1, N=256, K=256, W_dtype="uint4", fast_decoding=False),
+    dict(M=1, N=256, K=256, W_dtype="int4", group_size=-1, with_scaling=True),
+    dict(M=1, N=256, K=512, W_dtype="int4", group_size=128, with_scaling=True),
+    dict(M=1, N=256, K=512, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=1, N=256, K=512, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="rescale"),
+    dict(M=1, N=256, K=512, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    # C0 / C1 style
+    dict(M=1, N=1024, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=1, N=512, K=2048, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original", with_bias=True),
+    dict(M=1, N=512, K=1024, W_dtype="uint4", group_size=256, with_scaling=True, with_zeros=True, zeros_mode="original", int_zeros=False),
+    dict(M=3, N=512, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized", with_bias=True),
+    dict(M=8, N=256, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="rescale"),
+    dict(M=16, N=256, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=27, N=256, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=32, N=256, K=512, W_dtype="uint4", group_size=-1, with_scaling=True),
+    dict(M=1, N=256, K=1024, W_dtype="uint2", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=5, N=256, K=1024, W_dtype="uint2", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=1, N=256, K=1024, W_dtype="int2", group_size=128, with_scaling=True),
+    dict(M=2, N=256, K=512, W_dtype="uint2", fast_decoding=False, group_size=128, with_scaling=True),
+    dict(M=1, N=256, K=1024, W_dtype="uint4", A_dtype="bfloat16", out_dtype="bfloat16", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=4, N=256, K=1024, W_dtype="uint4", A_dtype="bfloat16", out_dtype="bfloat16", fast_decoding=True, group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=1, N=256, K=1024, W_dtype="uint4", out_dtype="float32", accum_dtype="float32", group_size=128, with_scaling=True),
+]
+
+
+@pytest.mark.parametrize("kw", GEMV_CASES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_gemv_mma_parity(kw):
+    kw = dict(kw)
+    case = H.make_case(kw.pop("M"), kw.pop("N"), kw.pop("K"), **kw)
+    op, got, ref = _run(case, "gemv_mma")
+    H.assert_fp_close(got, ref, "gemv_mma")
+
+
+GEMM_CASES = [
+    # reference GEMM cases (test_general_matmul_ops_backend_tl.py:337-343), M=256 N=K=256
+    dict(M=256, N=256, K=256, W_dtype="uint4"),
+    dict(M=256, N=256, K=256, W_dtype="int4", group_size=-1, with_scaling=True),
+    dict(M=256, N=256, K=256, W_dtype="int4", group_size=64, with_scaling=True),
+    dict(M=256, N=256, K=256, W_dtype="uint4", group_size=64, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=256, N=256, K=256, W_dtype="uint4", group_size=64, with_scaling=True, with_zeros=True, zeros_mode="rescale"),
+    dict(M=256, N=256, K=256, W_dtype="uint4", group_size=64, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    # tile-shape coverage: BM = 32 / 64 / 128 / 256, ragged M, several n tiles, long K (pipeline wrap-around)
+    dict(M=33, N=128, K=512, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=64, N=256, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original", with_bias=True),
+    dict(M=100, N=256, K=2048, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized", with_bias=True),
+    dict(M=128, N=384, K=4096, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="rescale"),
+    dict(M=300, N=256, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original", int_zeros=False),
+    dict(M=512, N=512, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=128, N=256, K=1024, W_dtype="uint2", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=128, N=256, K=1024, W_dtype="int2", group_size=-1, with_scaling=True),
+    dict(M=128, N=256, K=1024, W_dtype="uint4", A_dtype="bfloat16", out_dtype="bfloat16", fast_decoding=True, group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=128, N=256, K=1024, W_dtype="uint4", out_dtype="float32", accum_dtype="float32", group_size=128, with_scaling=True),
+]
+
+
+@pytest.mark.parametrize("kw", GEMM_CASES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_gemm_tcgen05_parity(kw):
+    kw = dict(kw)
+    case = H.make_case(kw.pop("M"), kw.pop("N"), kw.pop("K"), **kw)
+    op, got, ref = _run(case, "gemm_ts_tcgen05")
+    H.assert_fp_close(got, ref, "gemm_ts")
+
+
+W2A8_CASES = [
+    dict(M=1, N=256, K=512, W_dtype="int2", out_dtype="int32"),
+    dict(M=1, N=256, K=1024, W_dtype="int2", out_dtype="float32"),
+    dict(M=7, N=256, K=1024, W_dtype="uint2", out_dtype="int32"),
+    dict(M=32, N=256, K=512, W_dtype="int2", out_dtype="int32"),
+    dict(M=16, N=256, K=512, W_dtype="int4", out_dtype="int32", fast_decoding=True),
+    dict(M=128, N=256, K=1024, W_dtype="int2", out_dtype="int32"),
+    dict(M=200, N=384, K=2048, W_dtype="int2", out_dtype="int32"),
+    dict(M=128, N=256, K=1024, W_dtype="uint2", out_dtype="int32"),
+    dict(M=64, N=128, K=512, W_dtype="int4", out_dtype="int32", fast_decoding=True),
+    dict(M=128, N=256, K=1024, W_dtype="int2", out_dtype="int8"),
+]
+
+
+@pytest.mark.parametrize("kw", W2A8_CASES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_int8_activation_bit_exact(kw):
+    kw = dict(kw)
+    M = kw["M"]
+    case = H.make_case(kw.pop("M"), kw.pop("N"), kw.pop("K"), A_dtype="int8", accum_dtype="int32", **kw)
+    op, got, ref = _run(case, "gemv_i8" if M <= 32 else "gemm_ts_tcgen05_i8")
+    assert torch.equal(got, ref)
+
+
+GENERIC_CASES = [
+    dict(M=1, N=64, K=256, W_dtype="nf4", group_size=64, with_scaling=True),
+    dict(M=5, N=64, K=256, W_dtype="fp4_e2m1", group_size=-1, with_scaling=True),
+    dict(M=2, N=64, K=256, W_dtype="e4m3_float8"),
+    dict(M=1, N=64, K=256, W_dtype="int1"),
+    dict(M=3, N=64, K=256, W_dtype="uint1", group_size=32, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=1, N=256, K=256, W_dtype="int4", group_size=32, with_scaling=True),   # reference GEMV case, g=32
+    dict(M=1, N=256, K=256, W_dtype="uint4", group_size=32, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=40, N=48, K=96, W_dtype="uint4", group_size=32, with_scaling=True, with_zeros=True, zeros_mode="rescale"),
+    dict(M=9, N=64, K=256, W_dtype="uint4", A_dtype="bfloat16", out_dtype="bfloat16", group_size=64, with_scaling=True),
+    dict(M=6, N=64, K=256, W_dtype="int8", A_dtype="float16"),
+]
+
+
+@pytest.mark.parametrize("kw", GENERIC_CASES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_generic_kernel_parity(kw):
+    kw = dict(kw)
+    case = H.make_case(kw.pop("M"), kw.pop("N"), kw.pop("K"), **kw)
+    if case["fmt"] == "fp_e4m3":  # keep to normal e4m3 codes (the reference's bit trick is wrong for 0/subnormals)
+        f = case["fields"]
+        case["fields"] = torch.where((f & 0x78) == 0, f | 0x08, f)
+        case["fields"] = torch.where((case["fields"] & 0x7F) == 0x7F, case["fields"] & 0xF7, case["fields"])
+    op, got, ref = _run(case, "generic_simt")
+    H.assert_fp_close(got, ref, "generic")
+
+
+def test_fast_kernels_agree_with_generic_on_device():
+    """on-device cross check: same inputs through the forced generic kernel and the auto-dispatched one."""
+    from bitblas_b200 import _lib
+    lib = _lib.load()
+    for M in (1, 16, 128):
+        case = H.make_case(M, 256, 1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True,
+                           zeros_mode="quantized", with_bias=True, seed=M)
+        op = H.product_operator(case)
+        fast = H.run_product(op, case)
+        prev = lib.bb_set_kernel_override(_lib.BB_KERNEL_GENERIC)
+        try:
+            slow = H.run_product(op, case)
+        finally:
+            lib.bb_set_kernel_override(prev)
+        H.assert_fp_close(fast, slow, f"fast-vs-generic M={M}")
+
+
+def test_empty_and_error_paths():
+    case = H.make_case(4, 256, 512, W_dtype="uint4", group_size=128, with_scaling=True)
+    op = H.product_operator(case, M=[1, 16])
+    W = H.product_weight(op, case)
+    s = case["scale"].cuda()
+    out = op(torch.empty((0, 512), dtype=torch.float16, device="cuda"), W, scale=s)
+    assert out.shape == (0, 256)
+    with pytest.raises(RuntimeError):
+        op(case["A"], W, scale=s)                     # CPU activations: no CPU path
+    with pytest.raises(ValueError):
+        op(case["A"].cuda()[:, :256].contiguous(), W, scale=s)   # wrong K
+    with pytest.raises(ValueError):
+        op(case["A"].cuda(), W)                        # missing scale
+    with pytest.raises(TypeError):
+        op(case["A"].cuda().float(), W, scale=s)       # wrong dtype
+
+
+def test_linear_module_and_state_dict_roundtrip():
+    import bitblas_b200 as bitblas
+    case = H.make_case(8, 256, 1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True,
+                       zeros_mode="quantized", with_bias=True)
+    lin = bitblas.Linear(1024, 256, bias=True, A_dtype="float16", W_dtype="uint4", accum_dtype="float16", out_dtype="float16",
+                         group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized", enable_tuning=False).cuda()
+    lin.load_and_transform_weight(case["fields"].to(torch.int8).cuda(), scales=case["scale"].cuda(),
+                                  zeros=case["zeros"].cuda(), bias=case["bias"].cuda())
+    ref = H.oracle_output(case)
+    got = lin(case["A"].cuda()).cpu()
+    H.assert_fp_close(got, ref, "Linear")
+    # 3-d input (batch, seq, K) -> m = batch*seq (module/__init__.py:282-284)
+    got3 = lin(case["A"].cuda().reshape(2, 4, 1024)).cpu().reshape(8, 256)
+    assert torch.equal(got3, got)
+    lin2 = bitblas.Linear(1024, 256, bias=True, A_dtype="float16", W_dtype="uint4", group_size=128, with_scaling=True,
+                          with_zeros=True, zeros_mode="quantized", enable_tuning=False)
+    lin2.load_state_dict(lin.state_dict())
+    assert torch.equal(lin2.cuda()(case["A"].cuda()).cpu(), got)
+
+
+def test_gptq_repack_device_matches_reference_loops():
+    """bb_repack_gptq_*_device vs the reference's python unpack (module/__init__.py:24-74) restated in the oracle."""
+    import bitblas_oracle as O
+    import numpy as np
+    import bitblas_b200 as bitblas
+    torch.manual_seed(0)
+    K, N, g, bits = 512, 256, 128, 4
+    intw = torch.randint(0, 16, (K, N), dtype=torch.int32)     # GPTQ: [K, N]
+    qweight = torch.zeros((K * bits // 32, N), dtype=torch.int32)
+    for k in range(K):
+        qweight[k // 8] |= intw[k] << (4 * (k % 8))
+    zint = torch.randint(0, 15, (K // g, N), dtype=torch.int32)
+    qzeros = torch.zeros((K // g, N * bits // 32), dtype=torch.int32)
+    for n in range(N):
+        qzeros[:, n // 8] |= zint[:, n] << (4 * (n % 8))
+    scales = (torch.rand(K // g, N) * 0.1 + 0.01).half()
+
+    class G:  # minimal stand-in for an auto_gptq QuantLinear
+        pass
+    gm = G(); gm.qweight = qweight; gm.qzeros = qzeros; gm.scales = scales; gm.bias = None
+    for mode in ("original", "rescale", "quantized"):
+        lin = bitblas.Linear(K, N, A_dtype="float16", W_dtype="uint4", group_size=g, with_scaling=True, with_zeros=True,
+                             zeros_mode=mode, enable_tuning=False).cuda()
+        lin.repack_from_gptq(gm)
+        fields = intw.T.contiguous()                              # [N, K]
+        exp_w = O.transform_weight(fields.to(torch.int8), "uint4", "float16", fast_decoding=True)
+        assert torch.equal(lin.qweight.cpu(), exp_w)
+        zi = O.unpack_qzeros(qzeros, bits).T.contiguous()        # [N, G], +1 applied
+        if mode == "original":
+            assert torch.equal(lin.zeros.cpu(), zi.half())
+        elif mode == "rescale":
+            assert torch.equal(lin.zeros.cpu(), zi.half() * scales.T.contiguous())
+        else:
+            assert torch.equal(lin.zeros.cpu(), torch.from_numpy(O.general_compress(zi.T.contiguous().numpy(), bits)))
+        A = (torch.rand(4, K) - 0.5).half()
+        ref = O.matmul_dequant(A, fields, W_dtype="uint4", group_size=g, with_scaling=True, with_zeros=True,
+                               zeros_mode=mode, scale=scales.T.contiguous(), zeros=lin.zeros.cpu())
+        H.assert_fp_close(lin(A.cuda()).cpu(), ref, f"gptq-{mode}")
