@@ -30,7 +30,9 @@ namespace bb {
 namespace {
 
 constexpr int TS_ROWS = 128;    // weight rows per CTA = MMA M
-constexpr int DQ_WARPS = 8;
+constexpr int DQ_GROUPS = 2;                // dequant warp groups; group g decodes k-blocks kb = g (mod DQ_GROUPS)
+constexpr int DQ_WARPS_PER_GROUP = 8;       // 4 TMEM lane quadrants x 2 column halves
+constexpr int DQ_WARPS = DQ_GROUPS * DQ_WARPS_PER_GROUP;
 constexpr int TS_THREADS = (2 + DQ_WARPS) * 32;
 constexpr int TA_SLOTS = 4;     // TMEM operand slots (k-blocks the dequant warps may run ahead)
 
@@ -130,6 +132,13 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 // K-major, 128B-swizzled shared-memory operand descriptor (rows of 128 B, 8-row swizzle atoms = 1024 B)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -183,51 +192,78 @@ struct TsSmem {
   static constexpr int kWBytes = TS_ROWS * kPRB;
   static constexpr int kStageBytes = kActBytes + kWBytes;
   static constexpr int kStagesRaw = (220 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = (kStagesRaw > 8 ? 8 : kStagesRaw) & ~1;  // even: stage parity is static per dequant group
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
 };
 
-// decode `PRB/2` packed bytes (this thread's half of the k-block) into 16 registers of natural-k-order
-// operand data.  16-bit targets.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+// Per-group dequant constants (one weight row):  v = ((x - mz) [- z2]) * s2 [+ negz2]
+struct DqConst {
+  uint32_t mz_lo, mz_hi;  // decode magic + folded integer zero point, for even / odd nibble positions
+  uint32_t z2, s2, negz2;
+};
+
+// decode this thread's half of the k-block (PRB/2 packed bytes at shared address `src`) into 16 registers of
+// natural-k-order 16-bit operand pairs.  MODE: 0 none, 1 scale, 2 original, 3 rescale, 4 quantized.
 template <typename T, int BITS, int MODE>
-__device__ __forceinline__ void dequant_half_row(const uint8_t* src, uint32_t (&out)[16], uint32_t mz, uint32_t z2,
-                                                 uint32_t s2, uint32_t negz2) {
-  auto fin = [&](uint32_t x) -> uint32_t {
+__device__ __forceinline__ void dequant_half_row(uint32_t src, uint32_t (&out)[16], const DqConst& c) {
+  constexpr bool HI = std::is_same<T, __half>::value && BITS == 4;
+  constexpr uint32_t M = TypeTraits<T>::kMagic;
+  auto fin = [&](uint32_t x, uint32_t mz) -> uint32_t {
     uint32_t t = sub2<T>(x, mz);
     if constexpr (MODE == 0) return t;
-    if constexpr (MODE == 1 || MODE == 4) return mul2<T>(t, s2);
-    if constexpr (MODE == 2) return mul2<T>(sub2<T>(t, z2), s2);
-    if constexpr (MODE == 3) return fma2<T>(t, s2, negz2);
+    if constexpr (MODE == 1 || MODE == 4) return mul2<T>(t, c.s2);
+    if constexpr (MODE == 2) return mul2<T>(sub2<T>(t, c.z2), c.s2);
+    if constexpr (MODE == 3) return fma2<T>(t, c.s2, c.negz2);
     return t;
   };
   if constexpr (BITS == 4) {
-    const uint4 pk = *reinterpret_cast<const uint4*>(src);
+    const uint4 pk = lds128(src);
     const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      uint32_t h[4];
-      decode_u4x8_raw<T>(w[i], h);
+      if constexpr (HI) {
+        // odd nibbles extracted in place: mantissa bits 4..7 under exponent 2^6 (0x5400) read exactly 64 + u
+        const uint32_t x = w[i], y = w[i] >> 8;
+        out[4 * i + 0] = fin(lop3_and_or(x, 0x000f000fu, M), c.mz_lo);
+        out[4 * i + 1] = fin(lop3_and_or(x, 0x00f000f0u, 0x54005400u), c.mz_hi);
+        out[4 * i + 2] = fin(lop3_and_or(y, 0x000f000fu, M), c.mz_lo);
+        out[4 * i + 3] = fin(lop3_and_or(y, 0x00f000f0u, 0x54005400u), c.mz_hi);
+      } else {
+        uint32_t h[4];
+        decode_u4x8_raw<T>(w[i], h);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out[4 * i + j] = fin(h[j]);
+        for (int j = 0; j < 4; ++j) out[4 * i + j] = fin(h[j], c.mz_lo);
+      }
     }
   } else {
-    const uint2 pk = *reinterpret_cast<const uint2*>(src);
+    const uint2 pk = lds64(src);
     const uint32_t w[2] = {pk.x, pk.y};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       uint32_t h[8];
       decode_u2x16_raw_interleaved<T>(w[i], h);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) out[8 * i + j] = fin(h[j]);
+      for (int j = 0; j < 8; ++j) out[8 * i + j] = fin(h[j], c.mz_lo);
     }
   }
 }
 
 template <int BITS>
-__device__ __forceinline__ void dequant_half_row_i8(const uint8_t* src, uint32_t (&out)[16], uint32_t zp4) {
+__device__ __forceinline__ void dequant_half_row_i8(uint32_t src, uint32_t (&out)[16], uint32_t zp4) {
   if constexpr (BITS == 2) {
-    const uint4 pk = *reinterpret_cast<const uint4*>(src);
+    const uint4 pk = lds128(src);
     const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -237,8 +273,8 @@ __device__ __forceinline__ void dequant_half_row_i8(const uint8_t* src, uint32_t
       for (int j = 0; j < 4; ++j) out[4 * i + j] = zp4 ? bytes_sub_zp(h[j], zp4) : h[j];
     }
   } else {
-    const uint4 p0 = *reinterpret_cast<const uint4*>(src);
-    const uint4 p1 = *reinterpret_cast<const uint4*>(src + 16);
+    const uint4 p0 = lds128(src);
+    const uint4 p1 = lds128(src + 16);
     const uint32_t w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -284,7 +320,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < TA_SLOTS; ++i) { mbar_init(&a_ready[i], DQ_WARPS); mbar_init(&a_free[i], 1); }
+    for (int i = 0; i < TA_SLOTS; ++i) { mbar_init(&a_ready[i], DQ_WARPS_PER_GROUP); mbar_init(&a_free[i], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -297,12 +333,14 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      int s = 0;
+      uint32_t par = 1;  // parity of the "previous use" of the stage: first pass must not wait
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S;
-        if (kb >= S) mbar_wait(&empty[s], ((kb / S) - 1) & 1);
+        if (kb >= S) mbar_wait(&empty[s], par);
         mbar_arrive_expect_tx(&full[s], SM::kStageBytes);
         tma_load_2d(sA + s * SM::kActBytes, &tmA, kb * KB, m0, &full[s]);
         tma_load_2d(sW + s * SM::kWBytes, &tmW, kb * PRB, n0, &full[s]);
+        if (++s == S) { s = 0; par ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -316,10 +354,11 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t f = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
         idesc = (1u << 4) | (f << 7) | (f << 10) | (uint32_t(BM >> 3) << 17) | (uint32_t(TS_ROWS >> 4) << 24);
       }
+      int s = 0, t = 0;
+      uint32_t spar = 0, tpar = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S, t = kb % TA_SLOTS;
-        mbar_wait(&full[s], (kb / S) & 1);
-        mbar_wait(&a_ready[t], (kb / TA_SLOTS) & 1);
+        mbar_wait(&full[s], spar);
+        mbar_wait(&a_ready[t], tpar);
         tc_fence_after();
         const uint64_t bdesc = make_sw128_desc(smem_u32(sA + s * SM::kActBytes));
 #pragma unroll
@@ -329,83 +368,138 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_commit(&empty[s]);
         tc_commit(&a_free[t]);
+        if (++s == S) { s = 0; spar ^= 1; }
+        if (++t == TA_SLOTS) { t = 0; tpar ^= 1; }
       }
       tc_commit(acc_full);
     }
   } else {
     // ===== dequant warps (then epilogue) =====
-    const int quad = warp & 3;              // TMEM lane quadrant this warp may touch
-    const int half = (warp - 2) >> 2;       // which half of the k-block's columns
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may touch
+    const int half = ((warp - 2) >> 2) & 1;            // which half of the k-block's columns
+    const int grp = (warp - 2) / DQ_WARPS_PER_GROUP;   // which k-blocks (kb % DQ_GROUPS == grp)
     const int row = quad * 32 + lane;       // weight row inside the tile == TMEM lane
     const int n = n0 + row;
     const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
     constexpr uint32_t MAGIC = INT8 ? 0u : TypeTraits<typename std::conditional<INT8, __half, T>::type>::kMagic;
     using TF = typename std::conditional<INT8, __half, T>::type;  // float-ish type for the 16-bit path
 
-    uint32_t mz = MAGIC + uint32_t(p.zp_const) * 0x00010001u, z2 = 0, s2 = 0, negz2 = 0;
-    int cur_g = -1;
+    constexpr bool HI = !INT8 && std::is_same<TF, __half>::value && BITS == 4;
+    constexpr uint32_t MAGIC_HI = HI ? 0x54005400u : MAGIC;
+    constexpr int ZSH = HI ? 16 : 1;  // odd-nibble values are 64 + u: the folded zero point sits 4 mantissa bits up
+    static_assert(TA_SLOTS == 2 * DQ_GROUPS && (S % DQ_GROUPS) == 0, "slot / stage ownership is static per group");
     const int kb_per_g = p.g / KB;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % S, t = kb % TA_SLOTS;
-      if constexpr (!INT8) {
-        const int gi = kb / kb_per_g;
-        if (gi != cur_g && p.mode != 0) {
-          cur_g = gi;
-          const TF sv = reinterpret_cast<const TF*>(p.scale)[size_t(n) * p.G + gi];
-          s2 = dup2<TF>(sv);
-          if (p.mode == 2 || p.mode == 3) {
-            TF zv = reinterpret_cast<const TF*>(p.zeros)[size_t(n) * p.G + gi];
-            z2 = dup2<TF>(zv);
-            negz2 = z2 ^ 0x80008000u;
-          } else if (p.mode == 4) {
-            const uint8_t* qz = reinterpret_cast<const uint8_t*>(p.zeros) + size_t(gi) * (size_t(p.N) * BITS / 8);
-            constexpr int EPB = 8 / BITS;
-            const uint32_t zq = (qz[n / EPB] >> (BITS * (n % EPB))) & ((1u << BITS) - 1u);
-            mz = MAGIC + zq * 0x00010001u;
+    const uint16_t* sc_row = reinterpret_cast<const uint16_t*>(p.scale) + size_t(n) * p.G;
+    const uint16_t* z_row = reinterpret_cast<const uint16_t*>(p.zeros) + size_t(n) * p.G;
+    constexpr int EPB = 8 / BITS;
+    const uint8_t* qz_col = reinterpret_cast<const uint8_t*>(p.zeros) + n / EPB;
+    const size_t qz_stride = size_t(p.N) * BITS / 8;
+    const uint32_t qz_shift = BITS * (n % EPB);
+    const uint32_t src0 = smem_u32(sW) + row * PRB + half * (PRB / 2);
+    const uint32_t tdst0 = lane_addr + ACOL0 + half * 16;
+
+    auto dq_loop = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      DqConst c;
+      c.mz_lo = MAGIC + uint32_t(p.zp_const) * 0x00010001u;
+      c.mz_hi = MAGIC_HI + uint32_t(p.zp_const * ZSH) * 0x00010001u;
+      c.z2 = c.s2 = c.negz2 = 0;
+      // group parameters are fetched one needed-group ahead so their latency never sits in front of a decode
+      uint16_t s_raw = 0, z_raw = 0;
+      uint32_t qz_raw = 0;
+      auto fetch_group = [&](int gi) {
+        if constexpr (MODE != 0) s_raw = __ldg(sc_row + gi);
+        if constexpr (MODE == 2 || MODE == 3) z_raw = __ldg(z_row + gi);
+        if constexpr (MODE == 4) qz_raw = __ldg(qz_col + size_t(gi) * qz_stride);
+      };
+      int gi = grp / kb_per_g;           // group of this warp's first k-block
+      int g_end = (gi + 1) * kb_per_g;   // first k-block of the next group
+      const int g_step = kb_per_g >= DQ_GROUPS ? 1 : DQ_GROUPS / kb_per_g;  // groups skipped per switch
+      bool fresh = true;
+      if constexpr (MODE != 0) fetch_group(gi);
+      int st = grp;                      // smem stage of kb (S % DQ_GROUPS == 0 keeps stage parity per group)
+      uint32_t full_par = 0;
+      uint32_t it = 0;                   // iteration count of this warp: slot = grp + DQ_GROUPS * (it & 1)
+      int prev_slot = -1;
+      for (int kb = grp; kb < num_kb; kb += DQ_GROUPS) {
+        if constexpr (MODE != 0) {
+          if (kb >= g_end) {
+            do { gi += 1; g_end += kb_per_g; } while (kb >= g_end);
+            fresh = true;
+          }
+          if (fresh) {
+            fresh = false;
+            c.s2 = uint32_t(s_raw) * 0x00010001u;
+            if constexpr (MODE == 2 || MODE == 3) {
+              c.z2 = uint32_t(z_raw) * 0x00010001u;
+              c.negz2 = c.z2 ^ 0x80008000u;
+            }
+            if constexpr (MODE == 4) {
+              const uint32_t zq = (qz_raw >> qz_shift) & ((1u << BITS) - 1u);
+              c.mz_lo = MAGIC + zq * 0x00010001u;
+              c.mz_hi = MAGIC_HI + (zq * ZSH) * 0x00010001u;
+            }
+            if (gi + g_step < p.G) fetch_group(gi + g_step);
           }
         }
-      }
-      mbar_wait(&full[s], (kb / S) & 1);
-      if (kb >= TA_SLOTS) {
-        mbar_wait(&a_free[t], ((kb / TA_SLOTS) - 1) & 1);
-        tc_fence_after();
-      }
-      const uint8_t* src = sW + s * SM::kWBytes + row * PRB + half * (PRB / 2);
-      uint32_t regs[16];
-      if constexpr (INT8) {
-        dequant_half_row_i8<BITS>(src, regs, uint32_t(p.zp_const) * 0x01010101u);
-      } else {
-        switch (p.mode) {
-          case 0: dequant_half_row<TF, BITS, 0>(src, regs, mz, z2, s2, negz2); break;
-          case 1: dequant_half_row<TF, BITS, 1>(src, regs, mz, z2, s2, negz2); break;
-          case 2: dequant_half_row<TF, BITS, 2>(src, regs, mz, z2, s2, negz2); break;
-          case 3: dequant_half_row<TF, BITS, 3>(src, regs, mz, z2, s2, negz2); break;
-          default: dequant_half_row<TF, BITS, 4>(src, regs, mz, z2, s2, negz2); break;
+        mbar_wait(&full[st], full_par);
+        uint32_t regs[16];
+        if constexpr (INT8) dequant_half_row_i8<BITS>(src0 + st * SM::kWBytes, regs, uint32_t(p.zp_const) * 0x01010101u);
+        else dequant_half_row<TF, BITS, MODE>(src0 + st * SM::kWBytes, regs, c);
+        // publish the PREVIOUS k-block's TMEM slot only now: its tcgen05.st had the whole decode above to land
+        if (prev_slot >= 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[prev_slot]);
         }
+        const int slot = grp + DQ_GROUPS * int(it & 1);
+        if (it >= 2) {
+          mbar_wait(&a_free[slot], ((it >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_x16(tdst0 + slot * 32, regs);
+        prev_slot = slot;
+        ++it;
+        st += DQ_GROUPS;
+        if (st >= S) { st -= S; full_par ^= 1; }
       }
-      tmem_st_x16(lane_addr + ACOL0 + t * 32 + half * 16, regs);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_ready[t]);
+      if (prev_slot >= 0) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[prev_slot]);
+      }
+    };
+    if constexpr (INT8) {
+      dq_loop(std::integral_constant<int, 0>{});
+    } else {
+      switch (p.mode) {
+        case 0: dq_loop(std::integral_constant<int, 0>{}); break;
+        case 1: dq_loop(std::integral_constant<int, 1>{}); break;
+        case 2: dq_loop(std::integral_constant<int, 2>{}); break;
+        case 3: dq_loop(std::integral_constant<int, 3>{}); break;
+        default: dq_loop(std::integral_constant<int, 4>{}); break;
+      }
     }
 
     // ----- epilogue: accumulator[lane = n, column = m] -> C[m, n] -----
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    constexpr int CPH = BM / 2;                  // columns per half
-    constexpr int CH = CPH < 16 ? CPH : 16;      // columns per tcgen05.ld (x16)
-    static_assert(CPH % CH == 0 && CH == 16, "BM must be >= 32");
+    constexpr int CPH = BM / (2 * DQ_GROUPS);    // accumulator columns per warp
+    constexpr int CH = CPH < 16 ? CPH : 16;      // columns per tcgen05.ld
+    static_assert(CPH % CH == 0 && (CH == 16 || CH == 8), "BM must be >= 32");
     float bias_f = 0.f;
     if (p.bias) {
       if (p.a_dtype == BB_F16) bias_f = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
       else if (p.a_dtype == BB_BF16) bias_f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
       else bias_f = float(reinterpret_cast<const int8_t*>(p.bias)[n]);
     }
-    for (int c0 = half * CPH; c0 < (half + 1) * CPH; c0 += CH) {
+    const int cbase = (grp * 2 + half) * CPH;
+    for (int c0 = cbase; c0 < cbase + CPH; c0 += CH) {
       if (m0 + c0 >= p.M) break;  // warp-uniform
       uint32_t v[16];
-      tmem_ld_x16(lane_addr + c0, v);
+      if constexpr (CH == 16) tmem_ld_x16(lane_addr + c0, v); else tmem_ld_x8(lane_addr + c0, v);
       tmem_wait_ld();
 #pragma unroll
       for (int c = 0; c < CH; ++c) {

@@ -3,24 +3,30 @@
 // Replaces the reference's generated SIMT GEMV (bitblas/ops/general_matmul/tilelang/dequantize/
 // gemv_dequantize_simt.py:164-262: 128-bit A loads, 4-byte packed-B loads, LOP3 decode, fp16 FMA /
 // __dp4a, shuffle all-reduce).  B200 design:
-//   * the packed weights are the only HBM stream that matters (N*K*bits/8 bytes); every warp owns 16
-//     weight rows and a contiguous K range, reads them with 128-bit ld.global.nc.L1::no_allocate, 4
-//     steps (4 KB / warp) in flight, every CTA resident at once so the memory system balances the tail;
-//   * LOP3 decode is done in registers straight into mma.sync fragments (m16n8k16 f16/bf16, m16n8k32
-//     u8.s8): 16 weight rows x 8 batch rows per instruction, fp32 / int32 accumulation, so the CUDA-core
-//     pipes only see the decode (1 LOP3 + 1 HSUB2 per two weights), not the FMAs;
+//   * the packed weights are the only HBM stream that matters (N*K*bits/8 bytes).  A warp owns 16 weight rows
+//     and a contiguous K range; KS warps (one CTA) split K for a row block.  KS is chosen on the host so that
+//     ~16 warps per SM are resident and EVERY CTA is resident at once: equal work per warp + a shared memory
+//     system means all CTAs drain together and there is no tail wave.  Each warp keeps PF=4 steps (4 KB) of
+//     128-bit ld.global.nc.L1::no_allocate loads in flight.
+//   * LOP3 decode goes straight into mma.sync fragments (m16n8k16 f16/bf16, m16n8k32 u8.s8): 16 weight rows x
+//     8 batch rows per instruction with fp32 / int32 accumulation, so the CUDA-core pipes only see the
+//     decode.  The "+1024" decode magic and the zero point are NOT subtracted per element: a second MMA with
+//     the constant fragment -(1024 + z[row]) against the same activations removes both inside the fp32
+//     accumulator (1 HMMA instead of 4 HSUB2 per 16 weights x 2 rows).
+//   * fp16 / 4-bit: odd nibbles are extracted in place (mask 0x00f000f0 -> 1024 + 16u) and paired with
+//     activations pre-scaled by 1/16, which removes two of the three shifts per 32-bit word.
 //   * k order inside a dot product is free, so the reference's interleaved storage layout AND the plain
-//     compressed layout are both consumed with zero re-ordering cost (the B fragment is permuted instead);
-//   * per-group scale / zero are applied to the group's partial sum (s * (sum(w*a) - z * sum(a))), the
-//     integer part of z folded into the decode magic so GPTQ-style integer zero points cost nothing.
+//     compressed layout are both consumed with zero re-ordering cost (the B fragment is permuted instead).
+//   * per-group scale is applied to the group's partial sum; non-integer zero points / "rescale" zeros use a
+//     third MMA against a ones fragment to obtain sum(a) per group.
 #include "bb_common.cuh"
 
 namespace bb {
 
 namespace {
 
-constexpr int GEMV_WARPS = 4;
-constexpr int PF = 4;  // weight steps in flight per warp
+constexpr int MAX_KS = 8;  // warps per CTA = K splits per 16-row block
+constexpr int PF = 6;      // cp.async stages per warp (PF-1 steps of weights in flight)
 
 struct GemvParams {
   const void* A;
@@ -36,38 +42,33 @@ struct GemvParams {
   int zmode;      // 0 none, 1 original, 2 rescale, 3 quantized
   int zp_const;   // constant zero point of the "int" formats (2^(bits-1)), 0 for uint
   int out_dtype;
-  int rb_per_cta; // 16-row blocks per CTA
+  int ks;         // warps per CTA
 };
 
 template <typename T>
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
 template <>
 __device__ __forceinline__ void mma_16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 template <>
 __device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void mma_16832_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 template <typename T>
-__device__ __forceinline__ float ld_as_float(const void* p, size_t i) {
-  return TypeTraits<T>::to_float(reinterpret_cast<const T*>(p)[i]);
+__device__ __forceinline__ float raw_to_float(uint16_t b) {
+  return TypeTraits<T>::to_float(*reinterpret_cast<const T*>(&b));
 }
-
-template <int BITS>
-struct WordsPerStep {  // 32 k per thread per step
-  static constexpr int value = BITS;  // 4-bit: 4 words (16 B), 2-bit: 2 words (8 B)
-};
 
 template <int BITS>
 __device__ __forceinline__ void load_w(const uint8_t* p, uint32_t (&w)[BITS]) {
@@ -80,201 +81,319 @@ __device__ __forceinline__ void load_w(const uint8_t* p, uint32_t (&w)[BITS]) {
   }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Weight staging: every thread copies exactly the bytes it will consume (its 32-k slice of rows r and r+8 of a step)
+// into its own shared-memory slot with cp.async, PF steps ahead.  In-flight HBM requests are then tracked by
+// cp.async groups instead of register scoreboards, so the L1-hit activation loads of the current step never wait
+// behind a DRAM round trip of a prefetch (the v1 register queue did: ~2 us per step, profiles/r1_v1_*).
+template <int BITS>
+__device__ __forceinline__ void stage_copy(uint32_t slot, const uint8_t* ga, const uint8_t* gb) {
+  if constexpr (BITS == 4) {
+    cp_async16(slot, ga);
+    cp_async16(slot + 512, gb);
+  } else {
+    cp_async8(slot, ga);
+    cp_async8(slot + 256, gb);
+  }
+}
+template <int BITS>
+__device__ __forceinline__ void stage_read(uint32_t slot, uint32_t (&wa)[BITS], uint32_t (&wb)[BITS]) {
+  if constexpr (BITS == 4) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wa[0]), "=r"(wa[1]), "=r"(wa[2]), "=r"(wa[3]) : "r"(slot));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wb[0]), "=r"(wb[1]), "=r"(wb[2]), "=r"(wb[3]) : "r"(slot + 512));
+  } else {
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wa[0]), "=r"(wa[1]) : "r"(slot));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wb[0]), "=r"(wb[1]) : "r"(slot + 256));
+  }
+}
+
+// split [0, total) into `parts` nearly equal contiguous ranges
+__device__ __forceinline__ void split_range(int total, int parts, int idx, int& begin, int& end) {
+  const int base = total / parts, rem = total % parts;
+  begin = idx * base + min(idx, rem);
+  end = begin + base + (idx < rem ? 1 : 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp16 / bf16 activations
 // ---------------------------------------------------------------------------------------------
-template <typename T, int BITS, bool IL, int NT>
-__global__ void __launch_bounds__(GEMV_WARPS * 32)
+template <typename T, int BITS, bool IL, int NT, int ZK>
+__global__ void __launch_bounds__(NT == 1 ? 128 : MAX_KS * 32) __maxnreg__(NT == 1 ? (ZK ? 112 : 80) : (NT == 2 ? (ZK ? 168 : 128) : (ZK ? 232 : 192)))
 gemv_mma_kernel(const GemvParams p) {
+  constexpr bool RS = ZK == 2;
   constexpr int NP = 32 / BITS / 2;     // pairs per 32-bit word: 4 (4-bit) or 8 (2-bit)
-  constexpr int WPS = BITS;             // words per thread per row per step
+  constexpr int WPS = BITS;             // 32-bit words per thread per row per step (32 k per thread)
+  constexpr bool HI = std::is_same<T, __half>::value && BITS == 4;  // in-place odd-nibble extraction
   constexpr uint32_t MAGIC = TypeTraits<T>::kMagic;
-  constexpr int MAXZ = TypeTraits<T>::kMagicVal - (1 << BITS);  // largest zero point that folds exactly
-  __shared__ float red[GEMV_WARPS][16][8 * NT];
+  constexpr uint32_t NEGMAGIC = MAGIC | 0x80008000u;
+  // odd nibbles sit at mantissa bits 4..7: with exponent 2^6 (0x5400) the fp16 value is exactly 64 + u
+  constexpr uint32_t MAGIC_HI = 0x54005400u;
+  constexpr uint32_t NEGMAGIC_HI = HI ? 0xd400d400u : NEGMAGIC;
+  constexpr int MAXZ = HI ? 47 : TypeTraits<T>::kMagicVal - (1 << BITS);  // largest zero point that folds exactly
+  constexpr uint32_t ONE2 = std::is_same<T, __half>::value ? 0x3c003c00u : 0x3f803f80u;
+  __shared__ float red[MAX_KS][16][8 * NT];
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform: keeps the loops below convergent
   const int r = lane >> 2, q = lane & 3;
-  const int nsteps_total = p.K / 128;
-  const int spw = (nsteps_total + GEMV_WARPS - 1) / GEMV_WARPS;
-  const int step_begin = warp * spw;
-  const int step_end = min(nsteps_total, step_begin + spw);
+  const int rb = blockIdx.x;
+  const int n_a = rb * 16 + r, n_b = n_a + 8;
+  int step_begin, step_end;
+  split_range(p.K / 128, p.ks, warp, step_begin, step_end);
+  const int ns = step_end - step_begin;
   const int spg = p.g / 128;  // steps per group
   const size_t row_bytes = size_t(p.K) * BITS / 8;
-  const T* Aptr = reinterpret_cast<const T*>(p.A);
-  constexpr uint32_t ONE2 = std::is_same<T, __half>::value ? 0x3c003c00u : 0x3f803f80u;
-  const uint32_t ones[4] = {ONE2, ONE2, ONE2, ONE2};
+  constexpr int STEP_BYTES = 16 * BITS;  // packed bytes per row per step
 
-  for (int rbi = 0; rbi < p.rb_per_cta; ++rbi) {
-    const int rb = blockIdx.x * p.rb_per_cta + rbi;
-    if (rb * 16 >= p.N) break;
-    const int n_a = rb * 16 + r, n_b = n_a + 8;
-    const uint8_t* wrow_a = p.W + size_t(n_a) * row_bytes + q * (4 * WPS);
-    const uint8_t* wrow_b = p.W + size_t(n_b) * row_bytes + q * (4 * WPS);
-
-    float acc_t[NT][4], acc_g[NT][4], asum_g[NT][4];
+  const uint8_t* wpa = p.W + size_t(n_a) * row_bytes + q * (4 * WPS) + size_t(step_begin) * STEP_BYTES;
+  const uint8_t* wpb = wpa + 8 * row_bytes;
+  // activations: this thread's 32-element slice of each step, as uint4 (8 elements each)
+  const uint4* ap[NT];
 #pragma unroll
-    for (int t = 0; t < NT; ++t)
+  for (int t = 0; t < NT; ++t) {
+    const int m = min(8 * t + r, p.M - 1);
+    ap[t] = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.A) + size_t(m) * p.K) + step_begin * 16 + q * 4;
+  }
+  const uint16_t* scale16 = reinterpret_cast<const uint16_t*>(p.scale);
+  const uint16_t* zeros16 = reinterpret_cast<const uint16_t*>(p.zeros);
+  const int row_off_a = n_a * p.G, row_off_b = row_off_a + 8 * p.G;  // [N, G] scale / zeros rows (N*G < 2^31)
+  constexpr int EPB = 8 / BITS;
+  const int qz_stride = p.N * BITS / 8;
+  const uint8_t* qz_base = reinterpret_cast<const uint8_t*>(p.zeros) + n_a / EPB;
+
+  float acc_t[NT][4], acc_g[NT][4], asum_g[RS ? NT : 1][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc_t[t][j] = acc_g[t][j] = asum_g[t][j] = 0.f;
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc_t[t][j] = acc_g[t][j] = 0.f;
+#pragma unroll
+  for (int t = 0; t < (RS ? NT : 1); ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) asum_g[t][j] = 0.f;
 
-    // per-group state
-    float s_a = 1.f, s_b = 1.f, zc_a = 0.f, zc_b = 0.f;
-    uint32_t mz_a = MAGIC + uint32_t(p.zp_const) * 0x00010001u, mz_b = mz_a;
-    bool need_asum = false;
+  // per-group state
+  float s_a = 1.f, s_b = 1.f, zc_a = 0.f, zc_b = 0.f;
+  uint32_t dzf[4] = {0u, 0u, 0u, 0u};  // -(z - rint(z)) fragment for non-integer "original" zero points
+  bool need_dz = false;
+  uint32_t fold[4];  // -(magic + z) fragment: {row a lo, row b lo, row a hi, row b hi}
+  {
+    const uint32_t z = uint32_t(p.zp_const);
+    fold[0] = fold[1] = NEGMAGIC + z * 0x00010001u;
+    fold[2] = fold[3] = NEGMAGIC_HI + (HI ? 16u * z : z) * 0x00010001u;
+  }
+  const uint32_t asum_frag[4] = {ONE2, ONE2, ONE2, ONE2};
+  int gi = step_begin / spg;
+  int grp_left = spg - (step_begin % spg);
 
-    auto begin_group = [&](int step) {
-      const int gi = step / spg;
-      if (p.with_scaling) {
-        s_a = ld_as_float<T>(p.scale, size_t(n_a) * p.G + gi);
-        s_b = ld_as_float<T>(p.scale, size_t(n_b) * p.G + gi);
+  auto set_fold = [&](uint32_t za, uint32_t zb) {
+    fold[0] = NEGMAGIC + za * 0x00010001u;
+    fold[1] = NEGMAGIC + zb * 0x00010001u;
+    fold[2] = NEGMAGIC_HI + (HI ? 16u * za : za) * 0x00010001u;
+    fold[3] = NEGMAGIC_HI + (HI ? 16u * zb : zb) * 0x00010001u;
+  };
+  // group parameters are fetched one group ahead (raw bits) so their L2 latency overlaps a whole step
+  uint16_t sr_a = 0, sr_b = 0, zr_a = 0, zr_b = 0;
+  auto fetch_group = [&](int g2) {
+    if (p.with_scaling) {
+      sr_a = __ldg(scale16 + row_off_a + g2);
+      sr_b = __ldg(scale16 + row_off_b + g2);
+    }
+    if (ZK != 0) {
+      zr_a = __ldg(zeros16 + row_off_a + g2);
+      zr_b = __ldg(zeros16 + row_off_b + g2);
+    } else if (p.zmode == 3) {
+      const uint8_t* qz = qz_base + g2 * qz_stride;
+      zr_a = __ldg(qz);
+      zr_b = __ldg(qz + 8 / EPB);
+    }
+  };
+  auto begin_group = [&]() {
+    if (p.with_scaling) {
+      s_a = raw_to_float<T>(sr_a);
+      s_b = raw_to_float<T>(sr_b);
+    }
+    if constexpr (ZK == 2) {       // "rescale": w * s - z  ->  s * sum(w a) - z * sum(a)
+      zc_a = raw_to_float<T>(zr_a);
+      zc_b = raw_to_float<T>(zr_b);
+    } else if constexpr (ZK == 1) {  // "original": (w - z) * s ; integer part folded, fraction via a third MMA
+      const float za = raw_to_float<T>(zr_a), zb = raw_to_float<T>(zr_b);
+      const float ia = rintf(za), ib = rintf(zb);
+      const bool oka = ia >= 0.f && ia <= float(MAXZ), okb = ib >= 0.f && ib <= float(MAXZ);
+      set_fold(oka ? uint32_t(int(ia)) : 0u, okb ? uint32_t(int(ib)) : 0u);
+      const float da = oka ? za - ia : za, db = okb ? zb - ib : zb;
+      need_dz = __any_sync(0xffffffffu, da != 0.f || db != 0.f);
+      if (need_dz) {
+        dzf[0] = dup2<T>(TypeTraits<T>::from_float(-da));
+        dzf[1] = dup2<T>(TypeTraits<T>::from_float(-db));
+        dzf[2] = dzf[0];
+        dzf[3] = dzf[1];
       }
-      if (p.zmode == 1 || p.zmode == 2) {
-        const float za = ld_as_float<T>(p.zeros, size_t(n_a) * p.G + gi);
-        const float zb = ld_as_float<T>(p.zeros, size_t(n_b) * p.G + gi);
-        if (p.zmode == 1) {
-          const float ia = rintf(za), ib = rintf(zb);
-          const bool oka = ia >= 0.f && ia <= float(MAXZ), okb = ib >= 0.f && ib <= float(MAXZ);
-          mz_a = MAGIC + (oka ? uint32_t(int(ia)) * 0x00010001u : 0u);
-          mz_b = MAGIC + (okb ? uint32_t(int(ib)) * 0x00010001u : 0u);
-          zc_a = (oka ? za - ia : za) * s_a;   // (w - z) * s = s*w - (s*z)
-          zc_b = (okb ? zb - ib : zb) * s_b;
-        } else {
-          zc_a = za; zc_b = zb;                // w * s - z
-        }
-        need_asum = __any_sync(0xffffffffu, zc_a != 0.f || zc_b != 0.f);
-      } else if (p.zmode == 3) {
-        const uint8_t* qz = reinterpret_cast<const uint8_t*>(p.zeros) + size_t(gi) * (size_t(p.N) * BITS / 8);
-        constexpr int EPB = 8 / BITS;
-        const uint32_t za = (qz[n_a / EPB] >> (BITS * (n_a % EPB))) & ((1u << BITS) - 1u);
-        const uint32_t zb = (qz[n_b / EPB] >> (BITS * (n_b % EPB))) & ((1u << BITS) - 1u);
-        mz_a = MAGIC + za * 0x00010001u;
-        mz_b = MAGIC + zb * 0x00010001u;
+    } else if (p.zmode == 3) {
+      set_fold((uint32_t(zr_a) >> (BITS * (n_a % EPB))) & ((1u << BITS) - 1u),
+               (uint32_t(zr_b) >> (BITS * (n_b % EPB))) & ((1u << BITS) - 1u));
+    }
+    if (gi + 1 < p.G) fetch_group(gi + 1);
+  };
+  auto end_group = [&]() {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = ((j < 2) ? s_a : s_b) * acc_g[t][j];
+        if constexpr (RS) v -= ((j < 2) ? zc_a : zc_b) * asum_g[t][j & 1];
+        acc_t[t][j] += v;
+        acc_g[t][j] = 0.f;
       }
-    };
-    auto end_group = [&]() {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float s = (j < 2) ? s_a : s_b;
-          float v = s * acc_g[t][j];
-          if (need_asum) v -= ((j < 2) ? zc_a : zc_b) * asum_g[t][j & 1];
-          acc_t[t][j] += v;
-          acc_g[t][j] = 0.f;
-        }
+      if constexpr (RS) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) asum_g[t][j] = 0.f;
       }
-    };
-
-    uint32_t wq[PF][2][WPS];
-#pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      if (step_begin + i < step_end) {
-        load_w<BITS>(wrow_a + size_t(step_begin + i) * (16 * BITS), wq[i][0]);
-        load_w<BITS>(wrow_b + size_t(step_begin + i) * (16 * BITS), wq[i][1]);
-      }
     }
+  };
 
-    bool group_open = false;
-    for (int s0 = step_begin; s0 < step_end; s0 += PF) {
-#pragma unroll
-      for (int i = 0; i < PF; ++i) {
-        const int step = s0 + i;
-        if (step >= step_end) break;
-        uint32_t wa[WPS], wb[WPS];
-#pragma unroll
-        for (int x = 0; x < WPS; ++x) { wa[x] = wq[i][0][x]; wb[x] = wq[i][1][x]; }
-        if (step + PF < step_end) {
-          load_w<BITS>(wrow_a + size_t(step + PF) * (16 * BITS), wq[i][0]);
-          load_w<BITS>(wrow_b + size_t(step + PF) * (16 * BITS), wq[i][1]);
-        }
-        if (!group_open || step % spg == 0) {
-          if (group_open) end_group();
-          begin_group(step);
-          group_open = true;
-        }
-        const int kq = step * 128 + q * 32;  // first k of this thread's 32-wide slice
-#pragma unroll
-        for (int wi = 0; wi < WPS; ++wi) {
-          uint32_t ha[NP], hb[NP];
-          if constexpr (BITS == 4) {
-            decode_u4x8_raw<T>(wa[wi], ha);
-            decode_u4x8_raw<T>(wb[wi], hb);
-          } else if constexpr (IL) {
-            decode_u2x16_raw_interleaved<T>(wa[wi], ha);
-            decode_u2x16_raw_interleaved<T>(wb[wi], hb);
-          } else {
-            decode_u2x16_raw_compressed<T>(wa[wi], ha);
-            decode_u2x16_raw_compressed<T>(wb[wi], hb);
-          }
-#pragma unroll
-          for (int x = 0; x < NP; ++x) { ha[x] = sub2<T>(ha[x], mz_a); hb[x] = sub2<T>(hb[x], mz_b); }
-          const int kw = kq + wi * (2 * NP);  // this word's first k
-#pragma unroll
-          for (int t = 0; t < NT; ++t) {
-            uint32_t R[NP];
-            const int m = 8 * t + r;
-            if (m < p.M) {
-              const uint4* ap = reinterpret_cast<const uint4*>(Aptr + size_t(m) * p.K + kw);
-#pragma unroll
-              for (int x = 0; x < NP / 4; ++x) {
-                uint4 v = __ldg(ap + x);
-                R[4 * x] = v.x; R[4 * x + 1] = v.y; R[4 * x + 2] = v.z; R[4 * x + 3] = v.w;
-              }
-            } else {
-#pragma unroll
-              for (int x = 0; x < NP; ++x) R[x] = 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < NP / 2; ++j) {
-              const uint32_t af[4] = {ha[2 * j], hb[2 * j], ha[2 * j + 1], hb[2 * j + 1]};
-              uint32_t b0, b1;
-              if constexpr (IL) {
-                b0 = R[2 * j]; b1 = R[2 * j + 1];
-              } else {
-                b0 = __byte_perm(R[j], R[j + NP / 2], 0x5410);
-                b1 = __byte_perm(R[j], R[j + NP / 2], 0x7632);
-              }
-              mma_16816<T>(acc_g[t], af, b0, b1);
-              if (need_asum) mma_16816<T>(asum_g[t], ones, b0, b1);
-            }
-          }
-        }
-      }
-    }
-    if (group_open) end_group();
-
-    // cross-warp reduction + epilogue
-    __syncthreads();  // protect `red` from the previous row block's readers
+  constexpr int RPS = WPS * NP;  // activation registers per step per batch tile (32 k = 16 half2)
+  uint32_t Rq[NT][RPS];
+  auto load_acts = [&]() {
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      red[warp][r][8 * t + 2 * q] = acc_t[t][0];
-      red[warp][r][8 * t + 2 * q + 1] = acc_t[t][1];
-      red[warp][r + 8][8 * t + 2 * q] = acc_t[t][2];
-      red[warp][r + 8][8 * t + 2 * q + 1] = acc_t[t][3];
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 16 * 8 * NT; idx += GEMV_WARPS * 32) {
-      const int row = idx & 15, m = idx >> 4;
-      if (m >= p.M) continue;
-      float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < GEMV_WARPS; ++w) v += red[w][row][m];
-      const int n = rb * 16 + row;
-      const size_t o = size_t(m) * p.N + n;
-      if (p.out_dtype == BB_F16) {
-        __half h = __float2half_rn(v);
-        if (p.bias) h = __hadd(h, __float2half_rn(ld_as_float<T>(p.bias, n)));
-        reinterpret_cast<__half*>(p.C)[o] = h;
-      } else if (p.out_dtype == BB_BF16) {
-        __nv_bfloat16 h = __float2bfloat16_rn(v);
-        if (p.bias) h = __hadd(h, __float2bfloat16_rn(ld_as_float<T>(p.bias, n)));
-        reinterpret_cast<__nv_bfloat16*>(p.C)[o] = h;
-      } else {
-        if (p.bias) v += ld_as_float<T>(p.bias, n);
-        reinterpret_cast<float*>(p.C)[o] = v;
+      for (int x = 0; x < RPS / 4; ++x) {
+        const uint4 v = __ldg(ap[t] + x);
+        Rq[t][4 * x] = v.x; Rq[t][4 * x + 1] = v.y; Rq[t][4 * x + 2] = v.z; Rq[t][4 * x + 3] = v.w;
       }
+      ap[t] += 16;
+    }
+  };
+  auto process = [&](const uint32_t (&wa)[WPS], const uint32_t (&wb)[WPS], bool more) {
+    // batch rows >= M read a clamped row: MMA output columns are independent and those are never stored
+    uint32_t Rc[NT][RPS];
+    if constexpr (NT == 1) {
+#pragma unroll
+      for (int x = 0; x < RPS; ++x) Rc[0][x] = Rq[0][x];
+      if (more) load_acts();  // next step's activations: a full step of decode + MMA hides the L1 latency
+    } else {
+      load_acts();
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int x = 0; x < RPS; ++x) Rc[t][x] = Rq[t][x];
+    }
+    if (grp_left == 0) {
+      end_group();
+      ++gi;
+      grp_left = spg;
+      begin_group();
+    }
+    --grp_left;
+#pragma unroll
+    for (int wi = 0; wi < WPS; ++wi) {
+      uint32_t ha[NP], hb[NP];
+      if constexpr (HI) {
+        const uint32_t xa = wa[wi], ya = wa[wi] >> 8, xb = wb[wi], yb = wb[wi] >> 8;
+        ha[0] = lop3_and_or(xa, 0x000f000fu, MAGIC); ha[1] = lop3_and_or(xa, 0x00f000f0u, MAGIC_HI);
+        ha[2] = lop3_and_or(ya, 0x000f000fu, MAGIC); ha[3] = lop3_and_or(ya, 0x00f000f0u, MAGIC_HI);
+        hb[0] = lop3_and_or(xb, 0x000f000fu, MAGIC); hb[1] = lop3_and_or(xb, 0x00f000f0u, MAGIC_HI);
+        hb[2] = lop3_and_or(yb, 0x000f000fu, MAGIC); hb[3] = lop3_and_or(yb, 0x00f000f0u, MAGIC_HI);
+      } else if constexpr (BITS == 4) {
+        decode_u4x8_raw<T>(wa[wi], ha);
+        decode_u4x8_raw<T>(wb[wi], hb);
+      } else if constexpr (IL) {
+        decode_u2x16_raw_interleaved<T>(wa[wi], ha);
+        decode_u2x16_raw_interleaved<T>(wb[wi], hb);
+      } else {
+        decode_u2x16_raw_compressed<T>(wa[wi], ha);
+        decode_u2x16_raw_compressed<T>(wb[wi], hb);
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const uint32_t* R = &Rc[t][wi * NP];
+#pragma unroll
+        for (int j = 0; j < NP / 2; ++j) {
+          const uint32_t af[4] = {ha[2 * j], hb[2 * j], ha[2 * j + 1], hb[2 * j + 1]};
+          uint32_t b0, b1;
+          if constexpr (IL) {
+            b0 = R[2 * j]; b1 = R[2 * j + 1];
+          } else {
+            b0 = __byte_perm(R[j], R[j + NP / 2], 0x5410);
+            b1 = __byte_perm(R[j], R[j + NP / 2], 0x7632);
+          }
+          mma_16816<T>(acc_g[t], af, b0, b1);
+          mma_16816<T>(acc_g[t], fold, b0, b1);
+          if constexpr (ZK == 2) mma_16816<T>(asum_g[t], asum_frag, b0, b1);
+          if constexpr (ZK == 1) {
+            if (need_dz) mma_16816<T>(acc_g[t], dzf, b0, b1);
+          }
+        }
+      }
+    }
+  };
+
+  if (ns > 0) {
+    fetch_group(gi);
+    begin_group();
+    if constexpr (NT == 1) load_acts();
+    // cp.async ring: stage (s % PF) holds step s; PF-1 steps are in flight while one is consumed
+    extern __shared__ __align__(16) uint8_t stage_smem[];
+    constexpr int STAGE_BYTES = 64 * 4 * WPS;  // 2 rows x 32 lanes x (4*WPS) bytes
+    const uint32_t my_slot = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * (PF * STAGE_BYTES) + lane * (4 * WPS);
+#pragma unroll
+    for (int i = 0; i < PF - 1; ++i) {
+      if (i < ns) stage_copy<BITS>(my_slot + i * STAGE_BYTES, wpa + size_t(i) * STEP_BYTES, wpb + size_t(i) * STEP_BYTES);
+      cp_async_commit();
+    }
+    int slot_r = 0, slot_w = PF - 1;
+    const uint8_t* wnext_a = wpa + size_t(PF - 1) * STEP_BYTES;
+    const uint8_t* wnext_b = wpb + size_t(PF - 1) * STEP_BYTES;
+    for (int s = 0; s < ns; ++s) {
+      if (s + PF - 1 < ns) stage_copy<BITS>(my_slot + slot_w * STAGE_BYTES, wnext_a, wnext_b);
+      wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
+      cp_async_commit();
+      cp_async_wait<PF - 1>();
+      uint32_t wa[WPS], wb[WPS];
+      stage_read<BITS>(my_slot + slot_r * STAGE_BYTES, wa, wb);
+      process(wa, wb, s + 1 < ns);
+      slot_r = (slot_r + 1 == PF) ? 0 : slot_r + 1;
+      slot_w = (slot_w + 1 == PF) ? 0 : slot_w + 1;
+    }
+    end_group();
+  }
+
+  // cross-warp reduction + epilogue
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    red[warp][r][8 * t + 2 * q] = acc_t[t][0];
+    red[warp][r][8 * t + 2 * q + 1] = acc_t[t][1];
+    red[warp][r + 8][8 * t + 2 * q] = acc_t[t][2];
+    red[warp][r + 8][8 * t + 2 * q + 1] = acc_t[t][3];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 16 * 8 * NT; idx += blockDim.x) {
+    const int row = idx & 15, m = idx >> 4;
+    if (m >= p.M) continue;
+    float v = 0.f;
+    for (int w = 0; w < p.ks; ++w) v += red[w][row][m];
+    const int n = rb * 16 + row;
+    const size_t o = size_t(m) * p.N + n;
+    const float bf = p.bias ? TypeTraits<T>::to_float(reinterpret_cast<const T*>(p.bias)[n]) : 0.f;
+    if (p.out_dtype == BB_F16) {
+      __half h = __float2half_rn(v);
+      if (p.bias) h = __hadd(h, __float2half_rn(bf));
+      reinterpret_cast<__half*>(p.C)[o] = h;
+    } else if (p.out_dtype == BB_BF16) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      if (p.bias) h = __hadd(h, __float2bfloat16_rn(bf));
+      reinterpret_cast<__nv_bfloat16*>(p.C)[o] = h;
+    } else {
+      reinterpret_cast<float*>(p.C)[o] = v + bf;
     }
   }
 }
@@ -285,117 +404,116 @@ gemv_mma_kernel(const GemvParams p) {
 // produced on the tensor cores with an all-ones A fragment.
 // ---------------------------------------------------------------------------------------------
 template <int BITS, int NT>
-__global__ void __launch_bounds__(GEMV_WARPS * 32)
+__global__ void __launch_bounds__(NT == 1 ? 128 : MAX_KS * 32) __maxnreg__(NT == 1 ? 96 : (NT == 2 ? 128 : 208))
 gemv_i8_kernel(const GemvParams p) {
   constexpr int WPS = BITS;            // words per thread per row per step (32 k)
-  constexpr int RPW = 32 / BITS / 4;   // byte-quad registers per word: 4 (2-bit) or 2 (4-bit)
-  __shared__ int red[GEMV_WARPS][16][8 * NT];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int STEP_BYTES = 16 * BITS;
+  __shared__ int red[MAX_KS][16][8 * NT];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int r = lane >> 2, q = lane & 3;
-  const int nsteps_total = p.K / 128;
-  const int spw = (nsteps_total + GEMV_WARPS - 1) / GEMV_WARPS;
-  const int step_begin = warp * spw;
-  const int step_end = min(nsteps_total, step_begin + spw);
+  const int rb = blockIdx.x;
+  const int n_a = rb * 16 + r;
+  int step_begin, step_end;
+  split_range(p.K / 128, p.ks, warp, step_begin, step_end);
+  const int ns = step_end - step_begin;
   const size_t row_bytes = size_t(p.K) * BITS / 8;
-  const int8_t* Aptr = reinterpret_cast<const int8_t*>(p.A);
+  const uint8_t* wpa = p.W + size_t(n_a) * row_bytes + q * (4 * WPS) + size_t(step_begin) * STEP_BYTES;
+  const uint8_t* wpb = wpa + 8 * row_bytes;
+  const uint4* ap[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int m = min(8 * t + r, p.M - 1);
+    ap[t] = reinterpret_cast<const uint4*>(reinterpret_cast<const int8_t*>(p.A) + size_t(m) * p.K) + step_begin * 8 + q * 2;
+  }
   const uint32_t ones[4] = {0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u};
+  int acc[NT][4], asum[NT][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = asum[t][j] = 0;
 
-  for (int rbi = 0; rbi < p.rb_per_cta; ++rbi) {
-    const int rb = blockIdx.x * p.rb_per_cta + rbi;
-    if (rb * 16 >= p.N) break;
-    const int n_a = rb * 16 + r, n_b = n_a + 8;
-    const uint8_t* wrow_a = p.W + size_t(n_a) * row_bytes + q * (4 * WPS);
-    const uint8_t* wrow_b = p.W + size_t(n_b) * row_bytes + q * (4 * WPS);
-    int acc[NT][4], asum[NT][4];
+  auto process = [&](const uint32_t (&wa)[WPS], const uint32_t (&wb)[WPS]) {
+    uint32_t da[8], db[8];  // 8 byte-quads = 32 k per row, natural k order
 #pragma unroll
-    for (int t = 0; t < NT; ++t)
+    for (int wi = 0; wi < WPS; ++wi) {
+      if constexpr (BITS == 2) {
+        uint32_t ta[4], tb[4];
+        decode_u2x16_to_u8(wa[wi], 0u, ta);
+        decode_u2x16_to_u8(wb[wi], 0u, tb);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[t][j] = asum[t][j] = 0;
-
-    uint32_t wq[PF][2][WPS];
+        for (int x = 0; x < 4; ++x) { da[4 * wi + x] = ta[x]; db[4 * wi + x] = tb[x]; }
+      } else {
+        uint32_t ta[2], tb[2];
+        decode_u4x8_to_u8(wa[wi], 0u, ta);
+        decode_u4x8_to_u8(wb[wi], 0u, tb);
 #pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      if (step_begin + i < step_end) {
-        load_w<BITS>(wrow_a + size_t(step_begin + i) * (16 * BITS), wq[i][0]);
-        load_w<BITS>(wrow_b + size_t(step_begin + i) * (16 * BITS), wq[i][1]);
+        for (int x = 0; x < 2; ++x) { da[2 * wi + x] = ta[x]; db[2 * wi + x] = tb[x]; }
       }
     }
-    for (int s0 = step_begin; s0 < step_end; s0 += PF) {
-#pragma unroll
-      for (int i = 0; i < PF; ++i) {
-        const int step = s0 + i;
-        if (step >= step_end) break;
-        uint32_t da[8], db[8];  // 8 byte-quads = 32 k per row, natural k order
-#pragma unroll
-        for (int wi = 0; wi < WPS; ++wi) {
-          if constexpr (BITS == 2) {
-            uint32_t ta[4], tb[4];
-            decode_u2x16_to_u8(wq[i][0][wi], 0u, ta);
-            decode_u2x16_to_u8(wq[i][1][wi], 0u, tb);
-#pragma unroll
-            for (int x = 0; x < 4; ++x) { da[4 * wi + x] = ta[x]; db[4 * wi + x] = tb[x]; }
-          } else {
-            uint32_t ta[2], tb[2];
-            decode_u4x8_to_u8(wq[i][0][wi], 0u, ta);
-            decode_u4x8_to_u8(wq[i][1][wi], 0u, tb);
-#pragma unroll
-            for (int x = 0; x < 2; ++x) { da[2 * wi + x] = ta[x]; db[2 * wi + x] = tb[x]; }
-          }
-        }
-        if (step + PF < step_end) {
-          load_w<BITS>(wrow_a + size_t(step + PF) * (16 * BITS), wq[i][0]);
-          load_w<BITS>(wrow_b + size_t(step + PF) * (16 * BITS), wq[i][1]);
-        }
-        const int kq = step * 128 + q * 32;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          uint32_t R[8];
-          const int m = 8 * t + r;
-          if (m < p.M) {
-            const uint4* ap = reinterpret_cast<const uint4*>(Aptr + size_t(m) * p.K + kq);
-            uint4 v0 = __ldg(ap), v1 = __ldg(ap + 1);
-            R[0] = v0.x; R[1] = v0.y; R[2] = v0.z; R[3] = v0.w;
-            R[4] = v1.x; R[5] = v1.y; R[6] = v1.z; R[7] = v1.w;
-          } else {
-#pragma unroll
-            for (int x = 0; x < 8; ++x) R[x] = 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t af[4] = {da[2 * j], db[2 * j], da[2 * j + 1], db[2 * j + 1]};
-            mma_16832_u8s8(acc[t], af, R[2 * j], R[2 * j + 1]);
-            if (p.zp_const) mma_16832_u8s8(asum[t], ones, R[2 * j], R[2 * j + 1]);
-          }
-        }
-      }
-    }
-    __syncthreads();
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
+      const uint4 v0 = __ldg(ap[t]), v1 = __ldg(ap[t] + 1);
+      const uint32_t R[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      ap[t] += 8;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[t][j] -= p.zp_const * asum[t][j & 1];
-      red[warp][r][8 * t + 2 * q] = acc[t][0];
-      red[warp][r][8 * t + 2 * q + 1] = acc[t][1];
-      red[warp][r + 8][8 * t + 2 * q] = acc[t][2];
-      red[warp][r + 8][8 * t + 2 * q + 1] = acc[t][3];
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 16 * 8 * NT; idx += GEMV_WARPS * 32) {
-      const int row = idx & 15, m = idx >> 4;
-      if (m >= p.M) continue;
-      int v = 0;
-#pragma unroll
-      for (int w = 0; w < GEMV_WARPS; ++w) v += red[w][row][m];
-      const int n = rb * 16 + row;
-      const int b = p.bias ? int(reinterpret_cast<const int8_t*>(p.bias)[n]) : 0;
-      const size_t o = size_t(m) * p.N + n;
-      switch (p.out_dtype) {
-        case BB_I32: reinterpret_cast<int*>(p.C)[o] = v + b; break;
-        case BB_I8: reinterpret_cast<int8_t*>(p.C)[o] = int8_t(int8_t(v) + b); break;
-        case BB_F32: reinterpret_cast<float*>(p.C)[o] = float(v) + float(b); break;
-        case BB_F16: reinterpret_cast<__half*>(p.C)[o] = __hadd(__int2half_rn(v), __int2half_rn(b)); break;
-        default: reinterpret_cast<__nv_bfloat16*>(p.C)[o] = __hadd(__int2bfloat16_rn(v), __int2bfloat16_rn(b));
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t af[4] = {da[2 * j], db[2 * j], da[2 * j + 1], db[2 * j + 1]};
+        mma_16832_u8s8(acc[t], af, R[2 * j], R[2 * j + 1]);
+        if (p.zp_const) mma_16832_u8s8(asum[t], ones, R[2 * j], R[2 * j + 1]);
       }
+    }
+  };
+
+  if (ns > 0) {
+    // cp.async ring: stage (s % PF) holds step s; PF-1 steps are in flight while one is consumed
+    extern __shared__ __align__(16) uint8_t stage_smem[];
+    constexpr int STAGE_BYTES = 64 * 4 * WPS;  // 2 rows x 32 lanes x (4*WPS) bytes
+    const uint32_t my_slot = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * (PF * STAGE_BYTES) + lane * (4 * WPS);
+#pragma unroll
+    for (int i = 0; i < PF - 1; ++i) {
+      if (i < ns) stage_copy<BITS>(my_slot + i * STAGE_BYTES, wpa + size_t(i) * STEP_BYTES, wpb + size_t(i) * STEP_BYTES);
+      cp_async_commit();
+    }
+    int slot_r = 0, slot_w = PF - 1;
+    const uint8_t* wnext_a = wpa + size_t(PF - 1) * STEP_BYTES;
+    const uint8_t* wnext_b = wpb + size_t(PF - 1) * STEP_BYTES;
+    for (int s = 0; s < ns; ++s) {
+      if (s + PF - 1 < ns) stage_copy<BITS>(my_slot + slot_w * STAGE_BYTES, wnext_a, wnext_b);
+      wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
+      cp_async_commit();
+      cp_async_wait<PF - 1>();
+      uint32_t wa[WPS], wb[WPS];
+      stage_read<BITS>(my_slot + slot_r * STAGE_BYTES, wa, wb);
+      process(wa, wb);
+      slot_r = (slot_r + 1 == PF) ? 0 : slot_r + 1;
+      slot_w = (slot_w + 1 == PF) ? 0 : slot_w + 1;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] -= p.zp_const * asum[t][j & 1];
+    red[warp][r][8 * t + 2 * q] = acc[t][0];
+    red[warp][r][8 * t + 2 * q + 1] = acc[t][1];
+    red[warp][r + 8][8 * t + 2 * q] = acc[t][2];
+    red[warp][r + 8][8 * t + 2 * q + 1] = acc[t][3];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 16 * 8 * NT; idx += blockDim.x) {
+    const int row = idx & 15, m = idx >> 4;
+    if (m >= p.M) continue;
+    int v = 0;
+    for (int w = 0; w < p.ks; ++w) v += red[w][row][m];
+    const int n = rb * 16 + row;
+    const int b = p.bias ? int(reinterpret_cast<const int8_t*>(p.bias)[n]) : 0;
+    const size_t o = size_t(m) * p.N + n;
+    switch (p.out_dtype) {
+      case BB_I32: reinterpret_cast<int*>(p.C)[o] = v + b; break;
+      case BB_I8: reinterpret_cast<int8_t*>(p.C)[o] = int8_t(int8_t(v) + b); break;
+      case BB_F32: reinterpret_cast<float*>(p.C)[o] = float(v) + float(b); break;
+      case BB_F16: reinterpret_cast<__half*>(p.C)[o] = __hadd(__int2half_rn(v), __int2half_rn(b)); break;
+      default: reinterpret_cast<__nv_bfloat16*>(p.C)[o] = __hadd(__int2bfloat16_rn(v), __int2bfloat16_rn(b));
     }
   }
 }
@@ -411,32 +529,47 @@ GemvParams make_params(const MatmulArgs& a) {
   p.zmode = d.with_zeros ? (d.zeros_mode + 1) : 0;
   p.zp_const = (d.w_fmt == BB_W_INT) ? (1 << (d.w_bits - 1)) : 0;
   p.out_dtype = d.out_dtype;
-  p.rb_per_cta = 1;
+  p.ks = 1;
   return p;
 }
 
-template <typename K>
-int pick_rb(K kernel, int n_blocks16) {
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, GEMV_WARPS * 32, 0) != cudaSuccess || occ < 1) occ = 4;
-  const int cap = device_sm_count() * occ;
-  return (n_blocks16 + cap - 1) / cap;
+// K splits per 16-row block: the largest warp count per CTA such that EVERY CTA of the grid is resident at once
+// (occupancy queried from the runtime for this kernel instantiation, cached).
+template <typename KernelT>
+int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_blocks, int steps, int stage_bytes) {
+  const int sms = device_sm_count();
+  for (int ks = max_ks; ks >= 1; --ks) {
+    if (ks > steps) continue;
+    if (occ_cache[ks] < 0) {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, ks * 32, size_t(ks) * PF * stage_bytes) != cudaSuccess) occ = 0;
+      occ_cache[ks] = occ;
+    }
+    if (row_blocks <= sms * occ_cache[ks]) return ks;
+  }
+  return 1;
 }
+
+#define BB_GEMV_GO(KERNEL, MAXKS)                                              \
+  {                                                                            \
+    static int occ_cache[MAX_KS + 1] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   \
+    p.ks = pick_ks(KERNEL, occ_cache, MAXKS, nb, p.K / 128, stage_bytes);      \
+    KERNEL<<<nb, p.ks * 32, p.ks * PF * stage_bytes, a.stream>>>(p);           \
+  }
 
 template <typename T, int BITS, bool IL>
 int launch_mma_nt(const MatmulArgs& a, GemvParams p) {
   const int nb = p.N / 16;
+  const int stage_bytes = 64 * 4 * BITS;
   const int nt = (p.M + 7) / 8;
-#define BB_GEMV_LAUNCH(NTV)                                                              \
-  {                                                                                      \
-    auto k = gemv_mma_kernel<T, BITS, IL, NTV>;                                          \
-    p.rb_per_cta = pick_rb(k, nb);                                                       \
-    k<<<(nb + p.rb_per_cta - 1) / p.rb_per_cta, GEMV_WARPS * 32, 0, a.stream>>>(p);      \
-  }
-  if (nt <= 1) BB_GEMV_LAUNCH(1)
-  else if (nt == 2) BB_GEMV_LAUNCH(2)
-  else BB_GEMV_LAUNCH(4)
-#undef BB_GEMV_LAUNCH
+#define BB_GEMV_NT(ZKV)                                                                  \
+  if (nt <= 1) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV>), 4)                     \
+  else if (nt == 2) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 2, ZKV>), MAX_KS)           \
+  else BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 4, ZKV>), MAX_KS)
+  if (p.zmode == 2) { BB_GEMV_NT(2) }
+  else if (p.zmode == 1) { BB_GEMV_NT(1) }
+  else { BB_GEMV_NT(0) }
+#undef BB_GEMV_NT
   BB_LAUNCH_CHECK();
   return 0;
 }
@@ -460,7 +593,11 @@ bool gemv_mma_supported(const bb_matmul_desc& d, int m) {
 }
 
 int launch_gemv_mma(const MatmulArgs& a) {
-  GemvParams p = make_params(a);
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15)) {
+    set_error("gemv: A and W must be 16-byte aligned");
+    return 5;
+  }
+  const GemvParams p = make_params(a);
   const bool il = a.d.w_layout == BB_LAYOUT_INTERLEAVED_16;
   const bool f16 = a.d.a_dtype == BB_F16;
   const int bits = a.d.w_bits;
@@ -484,21 +621,23 @@ bool gemv_i8_supported(const bb_matmul_desc& d, int m) {
 }
 
 int launch_gemv_i8(const MatmulArgs& a) {
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15)) {
+    set_error("gemv: A and W must be 16-byte aligned");
+    return 5;
+  }
   GemvParams p = make_params(a);
   const int nb = p.N / 16;
   const int nt = (p.M + 7) / 8;
-#define BB_GEMV_I8_LAUNCH(BITSV, NTV)                                                    \
-  {                                                                                      \
-    auto k = gemv_i8_kernel<BITSV, NTV>;                                                 \
-    p.rb_per_cta = pick_rb(k, nb);                                                       \
-    k<<<(nb + p.rb_per_cta - 1) / p.rb_per_cta, GEMV_WARPS * 32, 0, a.stream>>>(p);      \
-  }
+  const int stage_bytes = 64 * 4 * a.d.w_bits;
   if (a.d.w_bits == 2) {
-    if (nt <= 1) BB_GEMV_I8_LAUNCH(2, 1) else if (nt == 2) BB_GEMV_I8_LAUNCH(2, 2) else BB_GEMV_I8_LAUNCH(2, 4)
+    if (nt <= 1) BB_GEMV_GO((gemv_i8_kernel<2, 1>), 4)
+    else if (nt == 2) BB_GEMV_GO((gemv_i8_kernel<2, 2>), MAX_KS)
+    else BB_GEMV_GO((gemv_i8_kernel<2, 4>), MAX_KS)
   } else {
-    if (nt <= 1) BB_GEMV_I8_LAUNCH(4, 1) else if (nt == 2) BB_GEMV_I8_LAUNCH(4, 2) else BB_GEMV_I8_LAUNCH(4, 4)
+    if (nt <= 1) BB_GEMV_GO((gemv_i8_kernel<4, 1>), 4)
+    else if (nt == 2) BB_GEMV_GO((gemv_i8_kernel<4, 2>), MAX_KS)
+    else BB_GEMV_GO((gemv_i8_kernel<4, 4>), MAX_KS)
   }
-#undef BB_GEMV_I8_LAUNCH
   BB_LAUNCH_CHECK();
   return 0;
 }
