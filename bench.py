@@ -267,30 +267,37 @@ def main():
     launches = (lib.bb_launch_count() - launches0) * args.steps // (args.steps + max(3, args.warmup))
     value = total_bytes / (ms_step * 1e-3) / 1e9
 
-    # per-shape kernel time with an explicit L2 flush between launches (roofline of the dominant kernel)
+    # per-shape kernel time, cold L2: the launch cycles through enough read-only copies of the parameters that the
+    # working set (> 2x the 126 MB L2) can never be resident; no write-flush is used because dirty lines left in L2 by a
+    # flush kernel get written back DURING the timed kernel and are charged to it (measured: +10..25 us).
     per_shape = []
     flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
     for op, prm, A, out, N, K in ops:
+        wbytes = prm["W"].numel()
+        ncopies = max(2, -(-300 * 1024 * 1024 // wbytes))
+        copies = [prm] + [{k: (v.clone() if v is not None else None) for k, v in prm.items()} for _ in range(ncopies - 1)]
+        for c in copies:
+            op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
+        torch.cuda.synchronize()
         ts = []
-        for _ in range(3):
-            op.forward(A, prm["W"], scale=prm["scale"], zeros=prm["zeros"], output=out)
-        for _ in range(10):
-            flush_l2(flush)
+        for i in range(4 * ncopies):
+            c = copies[i % ncopies]
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            op.forward(A, prm["W"], scale=prm["scale"], zeros=prm["zeros"], output=out)
+            op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
             e.record()
             torch.cuda.synchronize()
             ts.append(s.elapsed_time(e))
         t = statistics.median(ts)
         b = gemv_bytes(N // world, K)
         per_shape.append({"N": N, "K": K, "us": round(t * 1e3, 2), "GBps": round(b / (t * 1e-3) / 1e9, 1),
-                          "frac_hbm": round(b / (t * 1e-3) / 1e9 / pk["hbm"], 3), "kernel": op.kernel_for(1)})
+                          "frac_hbm": round(b / (t * 1e-3) / 1e9 / pk["hbm"], 3), "kernel": op.kernel_for(1), "copies": ncopies})
+        del copies
     tgt = per_shape[-1]
     roofline = {"bound": "hbm", "kernel": "gemv_mma_kernel<half,4,interleaved,NT=1> N=K=12288", "achieved": tgt["GBps"],
                 "peak": pk["hbm"], "unit": "GB/s", "frac": tgt["frac_hbm"], "traffic": None,
                 "algorithmic_bytes": gemv_bytes(12288 // world, 12288), "us": tgt["us"], "peak_source": pk["src"],
-                "timing": "CUDA events, single launch, L2 flushed (256 MiB write) before each of 10 launches, median"}
+                "timing": "CUDA events around single launches cycling through >= 300 MB of read-only parameter copies (cold L2), median"}
     result["gemv_shapes"] = per_shape
 
     # ---------------- GEMM M=4096 (tensor-bound half of the metric) ----------------
@@ -375,7 +382,7 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": "w4a16_gemv_llama70b", "shapes_NK": GEMV_SHAPES, "M": 1, "W_dtype": "uint4", "group_size": GROUP,
                            "zeros_mode": "quantized", "parallelism": f"column-parallel x{world} + all-gather" if world > 1 else "single GPU",
-                           "l2": "step working set 357 MB cycles through the 126 MB L2 (inputs larger than L2); per-shape numbers flush L2 explicitly"},
+                           "l2": "step working set 357 MB cycles through the 126 MB L2 (inputs larger than L2); per-shape numbers rotate >= 300 MB of parameter copies"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         line.update(result)
         print(json.dumps(line), flush=True)

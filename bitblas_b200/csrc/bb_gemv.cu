@@ -19,6 +19,8 @@
 //     compressed layout are both consumed with zero re-ordering cost (the B fragment is permuted instead).
 //   * per-group scale is applied to the group's partial sum; non-integer zero points / "rescale" zeros use a
 //     third MMA against a ones fragment to obtain sum(a) per group.
+#include <cstdlib>
+
 #include "bb_common.cuh"
 
 namespace bb {
@@ -26,7 +28,10 @@ namespace bb {
 namespace {
 
 constexpr int MAX_KS = 8;  // warps per CTA = K splits per 16-row block
-constexpr int PF = 6;      // cp.async stages per warp (PF-1 steps of weights in flight)
+constexpr int PF = 4;      // weight steps in flight per warp (register queue of plain 128-bit ld.global.nc loads).
+                           // tools/membench.cu on B200, 12288^2 weights: this pattern (16 rows x 64 B per warp load,
+                           // depth 4, 3-4 K-splits) streams at 6.0-6.7 TB/s; the same addresses through cp.async
+                           // (LDGSTS) saturate at ~4.3 TB/s, a depth-8 queue at ~4.0 TB/s.
 
 struct GemvParams {
   const void* A;
@@ -125,9 +130,15 @@ __device__ __forceinline__ void split_range(int total, int parts, int idx, int& 
 
 // ---------------------------------------------------------------------------------------------
 // fp16 / bf16 activations
+//   ZK: 0 no zeros (constant zero point of the "int" formats only), 1 "original", 2 "rescale", 3 "quantized"
+//   SC: with_scaling
 // ---------------------------------------------------------------------------------------------
-template <typename T, int BITS, bool IL, int NT, int ZK>
-__global__ void __launch_bounds__(NT == 1 ? 128 : MAX_KS * 32) __maxnreg__(NT == 1 ? (ZK ? 112 : 80) : (NT == 2 ? (ZK ? 168 : 128) : (ZK ? 232 : 192)))
+//   AS: (NT == 1, M <= 4) activations are staged through shared memory with cp.async one PF-step chunk ahead and
+//       read with ld.shared.  Loads of one warp complete in order, so an L1-hit ld.global issued behind the weight
+//       prefetch would wait a full DRAM round trip every step (tools/membench.cu: +22..45 % time); ld.shared does not.
+template <typename T, int BITS, bool IL, int NT, int ZK, bool SC, bool AS>
+__global__ void __launch_bounds__(NT == 1 ? 128 : MAX_KS * 32)
+__maxnreg__(NT == 1 ? ((ZK == 1 || ZK == 2) ? 112 : 96) : (NT == 2 ? ((ZK == 1 || ZK == 2) ? 168 : 128) : ((ZK == 1 || ZK == 2) ? 232 : 192)))
 gemv_mma_kernel(const GemvParams p) {
   constexpr bool RS = ZK == 2;
   constexpr int NP = 32 / BITS / 2;     // pairs per 32-bit word: 4 (4-bit) or 8 (2-bit)
@@ -138,8 +149,11 @@ gemv_mma_kernel(const GemvParams p) {
   // odd nibbles sit at mantissa bits 4..7: with exponent 2^6 (0x5400) the fp16 value is exactly 64 + u
   constexpr uint32_t MAGIC_HI = 0x54005400u;
   constexpr uint32_t NEGMAGIC_HI = HI ? 0xd400d400u : NEGMAGIC;
+  constexpr uint32_t ZMUL_HI = HI ? 0x00100010u : 0x00010001u;  // zero point scaled into the odd-nibble position
   constexpr int MAXZ = HI ? 47 : TypeTraits<T>::kMagicVal - (1 << BITS);  // largest zero point that folds exactly
   constexpr uint32_t ONE2 = std::is_same<T, __half>::value ? 0x3c003c00u : 0x3f803f80u;
+  constexpr int EPB = 8 / BITS;
+  constexpr int STEP_BYTES = 16 * BITS;  // packed bytes per row per step
   __shared__ float red[MAX_KS][16][8 * NT];
 
   const int lane = threadIdx.x & 31;
@@ -152,7 +166,6 @@ gemv_mma_kernel(const GemvParams p) {
   const int ns = step_end - step_begin;
   const int spg = p.g / 128;  // steps per group
   const size_t row_bytes = size_t(p.K) * BITS / 8;
-  constexpr int STEP_BYTES = 16 * BITS;  // packed bytes per row per step
 
   const uint8_t* wpa = p.W + size_t(n_a) * row_bytes + q * (4 * WPS) + size_t(step_begin) * STEP_BYTES;
   const uint8_t* wpb = wpa + 8 * row_bytes;
@@ -163,18 +176,29 @@ gemv_mma_kernel(const GemvParams p) {
     const int m = min(8 * t + r, p.M - 1);
     ap[t] = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.A) + size_t(m) * p.K) + step_begin * 16 + q * 4;
   }
-  const uint16_t* scale16 = reinterpret_cast<const uint16_t*>(p.scale);
-  const uint16_t* zeros16 = reinterpret_cast<const uint16_t*>(p.zeros);
-  const int row_off_a = n_a * p.G, row_off_b = row_off_a + 8 * p.G;  // [N, G] scale / zeros rows (N*G < 2^31)
-  constexpr int EPB = 8 / BITS;
+  // running pointers to the NEXT group's parameters (scale / zeros rows are [N, G]; quantized zeros [G, N*bits/8])
+  int gi = step_begin / spg;
+  int grp_left = spg - (step_begin % spg);
+  const uint16_t* sp_a = reinterpret_cast<const uint16_t*>(p.scale) + size_t(n_a) * p.G + gi;
+  const uint16_t* zp_a = reinterpret_cast<const uint16_t*>(p.zeros) + size_t(n_a) * p.G + gi;
+  const int row8 = 8 * p.G;
   const int qz_stride = p.N * BITS / 8;
-  const uint8_t* qz_base = reinterpret_cast<const uint8_t*>(p.zeros) + n_a / EPB;
+  const uint8_t* qzp = reinterpret_cast<const uint8_t*>(p.zeros) + n_a / EPB + size_t(gi) * qz_stride;
+  const uint32_t qsh_a = BITS * (n_a % EPB), qsh_b = BITS * (n_b % EPB);
+  int groups_to_fetch = p.G - gi;
 
-  float acc_t[NT][4], acc_g[NT][4], asum_g[RS ? NT : 1][4];
+  // the 16 MMAs of a step are spread over NCH independent accumulator chains (weights / fold x j parity) so that the
+  // per-warp step latency is 4 dependent HMMAs instead of 16
+  constexpr int NCH = 2;
+  float acc_t[NT][4], acc_c[NT][NCH][4], asum_g[RS ? NT : 1][4];
 #pragma unroll
   for (int t = 0; t < NT; ++t)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc_t[t][j] = acc_g[t][j] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      acc_t[t][j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) acc_c[t][c][j] = 0.f;
+    }
 #pragma unroll
   for (int t = 0; t < (RS ? NT : 1); ++t)
 #pragma unroll
@@ -184,44 +208,44 @@ gemv_mma_kernel(const GemvParams p) {
   float s_a = 1.f, s_b = 1.f, zc_a = 0.f, zc_b = 0.f;
   uint32_t dzf[4] = {0u, 0u, 0u, 0u};  // -(z - rint(z)) fragment for non-integer "original" zero points
   bool need_dz = false;
-  uint32_t fold[4];  // -(magic + z) fragment: {row a lo, row b lo, row a hi, row b hi}
-  {
-    const uint32_t z = uint32_t(p.zp_const);
-    fold[0] = fold[1] = NEGMAGIC + z * 0x00010001u;
-    fold[2] = fold[3] = NEGMAGIC_HI + (HI ? 16u * z : z) * 0x00010001u;
-  }
-  const uint32_t asum_frag[4] = {ONE2, ONE2, ONE2, ONE2};
-  int gi = step_begin / spg;
-  int grp_left = spg - (step_begin % spg);
-
+  uint32_t fold[4];  // -(magic + z) fragment: {row a even, row b even, row a odd, row b odd nibble positions}
   auto set_fold = [&](uint32_t za, uint32_t zb) {
     fold[0] = NEGMAGIC + za * 0x00010001u;
     fold[1] = NEGMAGIC + zb * 0x00010001u;
-    fold[2] = NEGMAGIC_HI + (HI ? 16u * za : za) * 0x00010001u;
-    fold[3] = NEGMAGIC_HI + (HI ? 16u * zb : zb) * 0x00010001u;
+    fold[2] = NEGMAGIC_HI + za * ZMUL_HI;
+    fold[3] = NEGMAGIC_HI + zb * ZMUL_HI;
   };
+  set_fold(uint32_t(p.zp_const), uint32_t(p.zp_const));
+  const uint32_t asum_frag[4] = {ONE2, ONE2, ONE2, ONE2};
+
   // group parameters are fetched one group ahead (raw bits) so their L2 latency overlaps a whole step
   uint16_t sr_a = 0, sr_b = 0, zr_a = 0, zr_b = 0;
-  auto fetch_group = [&](int g2) {
-    if (p.with_scaling) {
-      sr_a = __ldg(scale16 + row_off_a + g2);
-      sr_b = __ldg(scale16 + row_off_b + g2);
-    }
-    if (ZK != 0) {
-      zr_a = __ldg(zeros16 + row_off_a + g2);
-      zr_b = __ldg(zeros16 + row_off_b + g2);
-    } else if (p.zmode == 3) {
-      const uint8_t* qz = qz_base + g2 * qz_stride;
-      zr_a = __ldg(qz);
-      zr_b = __ldg(qz + 8 / EPB);
+  auto fetch_group = [&]() {
+    if (groups_to_fetch > 0) {
+      if constexpr (SC) {
+        sr_a = __ldg(sp_a);
+        sr_b = __ldg(sp_a + row8);
+        ++sp_a;
+      }
+      if constexpr (ZK == 1 || ZK == 2) {
+        zr_a = __ldg(zp_a);
+        zr_b = __ldg(zp_a + row8);
+        ++zp_a;
+      }
+      if constexpr (ZK == 3) {
+        zr_a = __ldg(qzp);
+        zr_b = __ldg(qzp + 8 / EPB);
+        qzp += qz_stride;
+      }
+      --groups_to_fetch;
     }
   };
   auto begin_group = [&]() {
-    if (p.with_scaling) {
+    if constexpr (SC) {
       s_a = raw_to_float<T>(sr_a);
       s_b = raw_to_float<T>(sr_b);
     }
-    if constexpr (ZK == 2) {       // "rescale": w * s - z  ->  s * sum(w a) - z * sum(a)
+    if constexpr (ZK == 2) {         // "rescale": w * s - z  ->  s * sum(w a) - z * sum(a)
       zc_a = raw_to_float<T>(zr_a);
       zc_b = raw_to_float<T>(zr_b);
     } else if constexpr (ZK == 1) {  // "original": (w - z) * s ; integer part folded, fraction via a third MMA
@@ -237,21 +261,24 @@ gemv_mma_kernel(const GemvParams p) {
         dzf[2] = dzf[0];
         dzf[3] = dzf[1];
       }
-    } else if (p.zmode == 3) {
-      set_fold((uint32_t(zr_a) >> (BITS * (n_a % EPB))) & ((1u << BITS) - 1u),
-               (uint32_t(zr_b) >> (BITS * (n_b % EPB))) & ((1u << BITS) - 1u));
+    } else if constexpr (ZK == 3) {
+      set_fold((uint32_t(zr_a) >> qsh_a) & ((1u << BITS) - 1u), (uint32_t(zr_b) >> qsh_b) & ((1u << BITS) - 1u));
     }
-    if (gi + 1 < p.G) fetch_group(gi + 1);
+    fetch_group();
   };
   auto end_group = [&]() {
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float v = ((j < 2) ? s_a : s_b) * acc_g[t][j];
-        if constexpr (RS) v -= ((j < 2) ? zc_a : zc_b) * asum_g[t][j & 1];
-        acc_t[t][j] += v;
-        acc_g[t][j] = 0.f;
+        const float sj = (j < 2) ? s_a : s_b;
+        if constexpr (RS) acc_t[t][j] = fmaf(-((j < 2) ? zc_a : zc_b), asum_g[t][j & 1], acc_t[t][j]);
+        float g = acc_c[t][0][j];
+#pragma unroll
+        for (int c = 1; c < NCH; ++c) g += acc_c[t][c][j];
+        acc_t[t][j] = SC ? fmaf(sj, g, acc_t[t][j]) : acc_t[t][j] + g;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc_c[t][c][j] = 0.f;
       }
       if constexpr (RS) {
 #pragma unroll
@@ -261,35 +288,48 @@ gemv_mma_kernel(const GemvParams p) {
   };
 
   constexpr int RPS = WPS * NP;  // activation registers per step per batch tile (32 k = 16 half2)
-  uint32_t Rq[NT][RPS];
-  auto load_acts = [&]() {
+  constexpr int NBUF = 1;
+  uint32_t Rbuf[NBUF][NT][RPS];
+  // batch rows >= M read a clamped row: MMA output columns are independent and those are never stored
+  auto load_acts = [&](uint32_t (&dst)[NT][RPS]) {
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
 #pragma unroll
       for (int x = 0; x < RPS / 4; ++x) {
         const uint4 v = __ldg(ap[t] + x);
-        Rq[t][4 * x] = v.x; Rq[t][4 * x + 1] = v.y; Rq[t][4 * x + 2] = v.z; Rq[t][4 * x + 3] = v.w;
+        dst[t][4 * x] = v.x; dst[t][4 * x + 1] = v.y; dst[t][4 * x + 2] = v.z; dst[t][4 * x + 3] = v.w;
       }
       ap[t] += 16;
     }
   };
-  auto process = [&](const uint32_t (&wa)[WPS], const uint32_t (&wb)[WPS], bool more) {
-    // batch rows >= M read a clamped row: MMA output columns are independent and those are never stored
-    uint32_t Rc[NT][RPS];
-    if constexpr (NT == 1) {
-#pragma unroll
-      for (int x = 0; x < RPS; ++x) Rc[0][x] = Rq[0][x];
-      if (more) load_acts();  // next step's activations: a full step of decode + MMA hides the L1 latency
-    } else {
-      load_acts();
-#pragma unroll
-      for (int t = 0; t < NT; ++t)
-#pragma unroll
-        for (int x = 0; x < RPS; ++x) Rc[t][x] = Rq[t][x];
+  // ---- AS: per-warp staging buffer [2 chunks][M][PF steps][4 x 16-byte pieces][4 q]  (256 B per step per batch row)
+  extern __shared__ __align__(16) uint8_t act_smem[];
+  const int Ms = AS ? p.M : 0;
+  const uint32_t as_base = (uint32_t)__cvta_generic_to_shared(act_smem) + warp * (2 * Ms * PF * 256);
+  const uint32_t as_read = as_base + min(r, max(Ms, 1) - 1) * (PF * 256) + q * 16;  // + chunk*Ms*PF*256 + u*256 + x*64
+  auto stage_acts = [&](int chunk_first_step, int buf) {  // steps [first, first+PF) of this warp's range
+    if constexpr (AS) {
+      const uint8_t* abytes = reinterpret_cast<const uint8_t*>(p.A) + (size_t(step_begin) + chunk_first_step) * 256;
+      for (int pid = lane; pid < Ms * PF * 16; pid += 32) {
+        const int m = pid / (PF * 16), rem = pid % (PF * 16), u = rem >> 4, pp = rem & 15;
+        if (chunk_first_step + u < ns)
+          cp_async16(as_base + ((buf * Ms + m) * PF + u) * 256 + (pp & 3) * 64 + (pp >> 2) * 16,
+                     abytes + size_t(m) * p.K * sizeof(T) + u * 256 + pp * 16);
+      }
+      cp_async_commit();
     }
+  };
+  auto read_acts = [&](int buf, int u, uint32_t (&dst)[NT][RPS]) {
+    const uint32_t a = as_read + (buf * Ms * PF + u) * 256;
+#pragma unroll
+    for (int x = 0; x < RPS / 4; ++x)
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(dst[0][4 * x]), "=r"(dst[0][4 * x + 1]), "=r"(dst[0][4 * x + 2]), "=r"(dst[0][4 * x + 3])
+                   : "r"(a + x * 64));
+  };
+  auto process = [&](const uint32_t (&wa)[WPS], const uint32_t (&wb)[WPS], const uint32_t (&Rc)[NT][RPS]) {
     if (grp_left == 0) {
       end_group();
-      ++gi;
       grp_left = spg;
       begin_group();
     }
@@ -326,11 +366,13 @@ gemv_mma_kernel(const GemvParams p) {
             b0 = __byte_perm(R[j], R[j + NP / 2], 0x5410);
             b1 = __byte_perm(R[j], R[j + NP / 2], 0x7632);
           }
-          mma_16816<T>(acc_g[t], af, b0, b1);
-          mma_16816<T>(acc_g[t], fold, b0, b1);
+          constexpr int CW = 0, CF = NCH == 4 ? 2 : 1;   // chain bases: weights, fold
+          const int par = NCH == 4 ? (j & 1) : 0;
+          mma_16816<T>(acc_c[t][CW + par], af, b0, b1);
+          mma_16816<T>(acc_c[t][CF + par], fold, b0, b1);
           if constexpr (ZK == 2) mma_16816<T>(asum_g[t], asum_frag, b0, b1);
           if constexpr (ZK == 1) {
-            if (need_dz) mma_16816<T>(acc_g[t], dzf, b0, b1);
+            if (need_dz) mma_16816<T>(acc_c[t][CF + par], dzf, b0, b1);
           }
         }
       }
@@ -338,32 +380,43 @@ gemv_mma_kernel(const GemvParams p) {
   };
 
   if (ns > 0) {
-    fetch_group(gi);
-    begin_group();
-    if constexpr (NT == 1) load_acts();
-    // cp.async ring: stage (s % PF) holds step s; PF-1 steps are in flight while one is consumed
-    extern __shared__ __align__(16) uint8_t stage_smem[];
-    constexpr int STAGE_BYTES = 64 * 4 * WPS;  // 2 rows x 32 lanes x (4*WPS) bytes
-    const uint32_t my_slot = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * (PF * STAGE_BYTES) + lane * (4 * WPS);
+    // register queue: wq[u] holds step (s + u); it is refilled with step (s + u + PF) right after being consumed
+    uint32_t wq[PF][2][WPS];
+    const uint8_t* wnext_a = wpa;
+    const uint8_t* wnext_b = wpb;
 #pragma unroll
-    for (int i = 0; i < PF - 1; ++i) {
-      if (i < ns) stage_copy<BITS>(my_slot + i * STAGE_BYTES, wpa + size_t(i) * STEP_BYTES, wpb + size_t(i) * STEP_BYTES);
-      cp_async_commit();
-    }
-    int slot_r = 0, slot_w = PF - 1;
-    const uint8_t* wnext_a = wpa + size_t(PF - 1) * STEP_BYTES;
-    const uint8_t* wnext_b = wpb + size_t(PF - 1) * STEP_BYTES;
-    for (int s = 0; s < ns; ++s) {
-      if (s + PF - 1 < ns) stage_copy<BITS>(my_slot + slot_w * STAGE_BYTES, wnext_a, wnext_b);
+    for (int u = 0; u < PF; ++u) {
+      if (u < ns) { load_w<BITS>(wnext_a, wq[u][0]); load_w<BITS>(wnext_b, wq[u][1]); }
       wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
-      cp_async_commit();
-      cp_async_wait<PF - 1>();
-      uint32_t wa[WPS], wb[WPS];
-      stage_read<BITS>(my_slot + slot_r * STAGE_BYTES, wa, wb);
-      process(wa, wb, s + 1 < ns);
-      slot_r = (slot_r + 1 == PF) ? 0 : slot_r + 1;
-      slot_w = (slot_w + 1 == PF) ? 0 : slot_w + 1;
     }
+    fetch_group();   // first group's parameters: the only synchronous fetch, overlapped with the weight prologue
+    begin_group();
+    if constexpr (AS) stage_acts(0, 0);
+    // GUARD = false: the chunk and all of its refills are inside the range (no per-step predicates)
+    auto chunk = [&](auto guard_tag, int s, int buf) {
+      constexpr bool GUARD = decltype(guard_tag)::value;
+      if constexpr (AS) {
+        stage_acts(s + PF, buf ^ 1);   // next chunk's activations: in flight for a whole chunk
+        cp_async_wait<1>();            // this chunk's activations have landed ...
+        __syncwarp();                  // ... including the pieces copied by the other lanes
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (!GUARD || s + u < ns) {
+          if constexpr (AS) read_acts(buf, u, Rbuf[0]); else load_acts(Rbuf[0]);
+          process(wq[u][0], wq[u][1], Rbuf[0]);
+          if (!GUARD || s + u + PF < ns) { load_w<BITS>(wnext_a, wq[u][0]); load_w<BITS>(wnext_b, wq[u][1]); }
+          wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
+        }
+      }
+      if constexpr (AS) __syncwarp();  // all lanes done reading `buf` before it is overwritten two chunks later
+    };
+    int s = 0, buf = 0;
+#pragma unroll 1
+    for (; s + 2 * PF <= ns; s += PF, buf ^= 1) chunk(std::false_type{}, s, buf);
+#pragma unroll 1
+    for (; s < ns; s += PF, buf ^= 1) chunk(std::true_type{}, s, buf);
+    if constexpr (AS) cp_async_wait<0>();
     end_group();
   }
 
@@ -466,29 +519,30 @@ gemv_i8_kernel(const GemvParams p) {
   };
 
   if (ns > 0) {
-    // cp.async ring: stage (s % PF) holds step s; PF-1 steps are in flight while one is consumed
-    extern __shared__ __align__(16) uint8_t stage_smem[];
-    constexpr int STAGE_BYTES = 64 * 4 * WPS;  // 2 rows x 32 lanes x (4*WPS) bytes
-    const uint32_t my_slot = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * (PF * STAGE_BYTES) + lane * (4 * WPS);
+    uint32_t wq[PF][2][WPS];
+    const uint8_t* wnext_a = wpa;
+    const uint8_t* wnext_b = wpb;
 #pragma unroll
-    for (int i = 0; i < PF - 1; ++i) {
-      if (i < ns) stage_copy<BITS>(my_slot + i * STAGE_BYTES, wpa + size_t(i) * STEP_BYTES, wpb + size_t(i) * STEP_BYTES);
-      cp_async_commit();
-    }
-    int slot_r = 0, slot_w = PF - 1;
-    const uint8_t* wnext_a = wpa + size_t(PF - 1) * STEP_BYTES;
-    const uint8_t* wnext_b = wpb + size_t(PF - 1) * STEP_BYTES;
-    for (int s = 0; s < ns; ++s) {
-      if (s + PF - 1 < ns) stage_copy<BITS>(my_slot + slot_w * STAGE_BYTES, wnext_a, wnext_b);
+    for (int u = 0; u < PF; ++u) {
+      if (u < ns) { load_w<BITS>(wnext_a, wq[u][0]); load_w<BITS>(wnext_b, wq[u][1]); }
       wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
-      cp_async_commit();
-      cp_async_wait<PF - 1>();
-      uint32_t wa[WPS], wb[WPS];
-      stage_read<BITS>(my_slot + slot_r * STAGE_BYTES, wa, wb);
-      process(wa, wb);
-      slot_r = (slot_r + 1 == PF) ? 0 : slot_r + 1;
-      slot_w = (slot_w + 1 == PF) ? 0 : slot_w + 1;
     }
+    auto chunk = [&](auto guard_tag, int s) {
+      constexpr bool GUARD = decltype(guard_tag)::value;
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (!GUARD || s + u < ns) {
+          process(wq[u][0], wq[u][1]);
+          if (!GUARD || s + u + PF < ns) { load_w<BITS>(wnext_a, wq[u][0]); load_w<BITS>(wnext_b, wq[u][1]); }
+          wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
+        }
+      }
+    };
+    int s = 0;
+#pragma unroll 1
+    for (; s + 2 * PF <= ns; s += PF) chunk(std::false_type{}, s);
+#pragma unroll 1
+    for (; s < ns; s += PF) chunk(std::true_type{}, s);
   }
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
@@ -542,7 +596,7 @@ int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_bl
     if (ks > steps) continue;
     if (occ_cache[ks] < 0) {
       int occ = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, ks * 32, size_t(ks) * PF * stage_bytes) != cudaSuccess) occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, ks * 32, size_t(ks) * stage_bytes) != cudaSuccess) occ = 0;
       occ_cache[ks] = occ;
     }
     if (row_blocks <= sms * occ_cache[ks]) return ks;
@@ -552,23 +606,31 @@ int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_bl
 
 #define BB_GEMV_GO(KERNEL, MAXKS)                                              \
   {                                                                            \
-    static int occ_cache[MAX_KS + 1] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   \
+    static int occ_cache_store[5][MAX_KS + 1];                                 \
+    static bool occ_init = false;                                              \
+    if (!occ_init) { for (auto& row : occ_cache_store) for (int& v : row) v = -1; occ_init = true; } \
+    int (&occ_cache)[MAX_KS + 1] = occ_cache_store[stage_bytes ? (p.M <= 4 ? p.M : 0) : 0]; \
     p.ks = pick_ks(KERNEL, occ_cache, MAXKS, nb, p.K / 128, stage_bytes);      \
-    KERNEL<<<nb, p.ks * 32, p.ks * PF * stage_bytes, a.stream>>>(p);           \
+    KERNEL<<<nb, p.ks * 32, p.ks * stage_bytes, a.stream>>>(p);                \
   }
 
 template <typename T, int BITS, bool IL>
 int launch_mma_nt(const MatmulArgs& a, GemvParams p) {
+  static const bool as_env = [] { const char* e = getenv("BB_GEMV_AS"); return e ? atoi(e) != 0 : false; }();
+  const bool pp = as_env && p.M <= 4;             // activation staging through shared memory
   const int nb = p.N / 16;
-  const int stage_bytes = 64 * 4 * BITS;
+  const int stage_bytes = pp ? 2 * p.M * PF * 256 : 0;  // per warp
   const int nt = (p.M + 7) / 8;
-#define BB_GEMV_NT(ZKV)                                                                  \
-  if (nt <= 1) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV>), 4)                     \
-  else if (nt == 2) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 2, ZKV>), MAX_KS)           \
-  else BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 4, ZKV>), MAX_KS)
-  if (p.zmode == 2) { BB_GEMV_NT(2) }
-  else if (p.zmode == 1) { BB_GEMV_NT(1) }
-  else { BB_GEMV_NT(0) }
+#define BB_GEMV_NT(ZKV, SCV)                                                             \
+  if (nt <= 1 && pp) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV, SCV, true>), 4)    \
+  else if (nt <= 1) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV, SCV, false>), 4) \
+  else if (nt == 2) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 2, ZKV, SCV, false>), MAX_KS) \
+  else BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 4, ZKV, SCV, false>), MAX_KS)
+  if (!p.with_scaling) { BB_GEMV_NT(0, false) }
+  else if (p.zmode == 0) { BB_GEMV_NT(0, true) }
+  else if (p.zmode == 1) { BB_GEMV_NT(1, true) }
+  else if (p.zmode == 2) { BB_GEMV_NT(2, true) }
+  else { BB_GEMV_NT(3, true) }
 #undef BB_GEMV_NT
   BB_LAUNCH_CHECK();
   return 0;
@@ -628,7 +690,7 @@ int launch_gemv_i8(const MatmulArgs& a) {
   GemvParams p = make_params(a);
   const int nb = p.N / 16;
   const int nt = (p.M + 7) / 8;
-  const int stage_bytes = 64 * 4 * a.d.w_bits;
+  const int stage_bytes = 0;
   if (a.d.w_bits == 2) {
     if (nt <= 1) BB_GEMV_GO((gemv_i8_kernel<2, 1>), 4)
     else if (nt == 2) BB_GEMV_GO((gemv_i8_kernel<2, 2>), MAX_KS)
