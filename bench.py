@@ -108,16 +108,16 @@ def cpu_reference_gemv(N, K, reps, warmup=1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
-    fields = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int8)
-    packed = torch.from_numpy(O.general_compress(fields.numpy(), 4))        # stored form (compressed)
+    fields = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int32)
     scale = (torch.rand((N, K // GROUP), generator=g) * 0.1 + 0.01).half()
     zq = torch.randint(0, 16, (K // GROUP, N), generator=g, dtype=torch.int8)
     qz = torch.from_numpy(O.general_compress(zq.numpy(), 4))
     A = (torch.rand((1, K), generator=g) - 0.5).half()
 
+    # like the reference's test program (test_general_matmul_ops_backend_tl.py:227-273) the CPU path works on the
+    # un-packed int weight matrix [N, K]; only the quantized zeros are unpacked inside the step
     def step():
-        f = O.unpack_fields(packed, 4)
-        return O.matmul_dequant(A, f, W_dtype="uint4", group_size=GROUP, with_scaling=True, with_zeros=True,
+        return O.matmul_dequant(A, fields, W_dtype="uint4", group_size=GROUP, with_scaling=True, with_zeros=True,
                                 zeros_mode="quantized", scale=scale, zeros=qz)
 
     for _ in range(warmup):
@@ -129,7 +129,7 @@ def cpu_reference_gemv(N, K, reps, warmup=1):
         ts.append(time.perf_counter() - t0)
     t = statistics.median(ts)
     return dict(value=gemv_bytes(N, K) / t / 1e9, unit="GB/s", cores=cores, kind="port",
-                sample=f"W4A16 GEMV M=1 N={N} K={K} g={GROUP} quantized zeros: torch unpack + (w-z)*s fp16 + fp32 matmul, "
+                sample=f"W4A16 GEMV M=1 N={N} K={K} g={GROUP} quantized zeros: torch (w-z)*s in fp16 + fp32 matmul on the int weight matrix, "
                        f"median of {reps} reps, {t * 1e3:.1f} ms/rep", ms_per_step=t * 1e3)
 
 
@@ -279,15 +279,17 @@ def main():
         for c in copies:
             op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
         torch.cuda.synchronize()
+        # back-to-back launches (no idle-stream launch latency between the events), one pass = every copy once
         ts = []
-        for i in range(4 * ncopies):
-            c = copies[i % ncopies]
+        for _ in range(5):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
+            for i in range(2 * ncopies):
+                c = copies[i % ncopies]
+                op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
             e.record()
             torch.cuda.synchronize()
-            ts.append(s.elapsed_time(e))
+            ts.append(s.elapsed_time(e) / (2 * ncopies))
         t = statistics.median(ts)
         b = gemv_bytes(N // world, K)
         per_shape.append({"N": N, "K": K, "us": round(t * 1e3, 2), "GBps": round(b / (t * 1e-3) / 1e9, 1),
@@ -295,9 +297,10 @@ def main():
         del copies
     tgt = per_shape[-1]
     roofline = {"bound": "hbm", "kernel": "gemv_mma_kernel<half,4,interleaved,NT=1> N=K=12288", "achieved": tgt["GBps"],
-                "peak": pk["hbm"], "unit": "GB/s", "frac": tgt["frac_hbm"], "traffic": None,
+                "peak": pk["hbm"], "unit": "GB/s", "frac": tgt["frac_hbm"],
+                "traffic": 81.86e6 if world == 1 else None,  # dram read+write per launch, profiles/r1_gemv_mma_ncu_full.txt
                 "algorithmic_bytes": gemv_bytes(12288 // world, 12288), "us": tgt["us"], "peak_source": pk["src"],
-                "timing": "CUDA events around single launches cycling through >= 300 MB of read-only parameter copies (cold L2), median"}
+                "timing": "CUDA events around back-to-back launches cycling through >= 300 MB of read-only parameter copies (cold L2), per-launch average, median of 5"}
     result["gemv_shapes"] = per_shape
 
     # ---------------- GEMM M=4096 (tensor-bound half of the metric) ----------------
@@ -316,7 +319,8 @@ def main():
         result["gemm"] = {"M": M, "N": N, "K": K, "ms": round(ms, 4), "TFLOPS": round(tf, 1), "kernel": op.kernel_for(M),
                           "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": pk["tf"], "unit": "TFLOP/s",
                                        "frac": round(tf / pk["tf"], 3), "frac_of_sustained": round(tf / pk["tf_sustained"], 3) if pk["tf_sustained"] else None,
-                                       "traffic": None, "peak_source": pk["src"],
+                                       "traffic": 1275.6e6 if world == 1 else None,  # profiles/r1_gemm_ts_ncu_full.txt
+                                       "algorithmic_flops": 2.0 * M * N * K, "peak_source": pk["src"],
                                        "note": "A (100 MB) + W (75 MB) exceed L2; 10 back-to-back launches"}}
         small = []
         for m in (16, 128):
