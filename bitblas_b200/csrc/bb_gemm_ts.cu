@@ -216,9 +216,10 @@ struct DqConst {
 
 // decode this thread's half of the k-block (PRB/2 packed bytes at shared address `src`) into 16 registers of
 // natural-k-order 16-bit operand pairs.  MODE: 0 none, 1 scale, 2 original, 3 rescale, 4 quantized.
-template <typename T, int BITS, int MODE>
+// IL = LOP3-interleaved storage (fast_decoding); !IL = plain compressed storage, re-ordered with byte permutes.
+template <typename T, int BITS, int MODE, bool IL>
 __device__ __forceinline__ void dequant_half_row(uint32_t src, uint32_t (&out)[16], const DqConst& c) {
-  constexpr bool HI = std::is_same<T, __half>::value && BITS == 4;
+  constexpr bool HI = IL && std::is_same<T, __half>::value && BITS == 4;
   constexpr uint32_t M = TypeTraits<T>::kMagic;
   auto fin = [&](uint32_t x, uint32_t mz) -> uint32_t {
     uint32_t t = sub2<T>(x, mz);
@@ -240,11 +241,20 @@ __device__ __forceinline__ void dequant_half_row(uint32_t src, uint32_t (&out)[1
         out[4 * i + 1] = fin(lop3_and_or(x, 0x00f000f0u, 0x54005400u), c.mz_hi);
         out[4 * i + 2] = fin(lop3_and_or(y, 0x000f000fu, M), c.mz_lo);
         out[4 * i + 3] = fin(lop3_and_or(y, 0x00f000f0u, 0x54005400u), c.mz_hi);
-      } else {
+      } else if constexpr (IL) {
         uint32_t h[4];
         decode_u4x8_raw<T>(w[i], h);
 #pragma unroll
         for (int j = 0; j < 4; ++j) out[4 * i + j] = fin(h[j], c.mz_lo);
+      } else {
+        // compressed: nibbles e0..e7 in order.  bytes t = (e0,e2,e4,e6), u = (e1,e3,e5,e7)
+        constexpr uint32_t MB = (M >> 8) & 0xffu, MBYTES = MB * 0x01010101u;  // magic high byte (0x64 / 0x43)
+        const uint32_t t = w[i] & 0x0f0f0f0fu, u = (w[i] >> 4) & 0x0f0f0f0fu;
+        const uint32_t x = __byte_perm(t, u, 0x5140), y = __byte_perm(t, u, 0x7362);  // (e0,e1,e2,e3), (e4,e5,e6,e7)
+        out[4 * i + 0] = fin(__byte_perm(x, MBYTES, 0x4140), c.mz_lo);
+        out[4 * i + 1] = fin(__byte_perm(x, MBYTES, 0x4342), c.mz_lo);
+        out[4 * i + 2] = fin(__byte_perm(y, MBYTES, 0x4140), c.mz_lo);
+        out[4 * i + 3] = fin(__byte_perm(y, MBYTES, 0x4342), c.mz_lo);
       }
     }
   } else {
@@ -252,15 +262,32 @@ __device__ __forceinline__ void dequant_half_row(uint32_t src, uint32_t (&out)[1
     const uint32_t w[2] = {pk.x, pk.y};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      uint32_t h[8];
-      decode_u2x16_raw_interleaved<T>(w[i], h);
+      if constexpr (IL) {
+        uint32_t h[8];
+        decode_u2x16_raw_interleaved<T>(w[i], h);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) out[8 * i + j] = fin(h[j], c.mz_lo);
+        for (int j = 0; j < 8; ++j) out[8 * i + j] = fin(h[j], c.mz_lo);
+      } else {
+        // compressed: fields e0..e15 in order.  byte planes s_k = (e_k, e_{k+4}, e_{k+8}, e_{k+12})
+        constexpr uint32_t MB = (M >> 8) & 0xffu, MBYTES = MB * 0x01010101u;
+        const uint32_t s0 = w[i] & 0x03030303u, s1 = (w[i] >> 2) & 0x03030303u, s2 = (w[i] >> 4) & 0x03030303u,
+                       s3 = (w[i] >> 6) & 0x03030303u;
+        const uint32_t a01 = __byte_perm(s0, s1, 0x5140), a23 = __byte_perm(s2, s3, 0x5140);  // (e0,e1,e4,e5) (e2,e3,e6,e7)
+        const uint32_t b01 = __byte_perm(s0, s1, 0x7362), b23 = __byte_perm(s2, s3, 0x7362);  // (e8,e9,e12,e13) ...
+        out[8 * i + 0] = fin(__byte_perm(a01, MBYTES, 0x4140), c.mz_lo);
+        out[8 * i + 1] = fin(__byte_perm(a23, MBYTES, 0x4140), c.mz_lo);
+        out[8 * i + 2] = fin(__byte_perm(a01, MBYTES, 0x4342), c.mz_lo);
+        out[8 * i + 3] = fin(__byte_perm(a23, MBYTES, 0x4342), c.mz_lo);
+        out[8 * i + 4] = fin(__byte_perm(b01, MBYTES, 0x4140), c.mz_lo);
+        out[8 * i + 5] = fin(__byte_perm(b23, MBYTES, 0x4140), c.mz_lo);
+        out[8 * i + 6] = fin(__byte_perm(b01, MBYTES, 0x4342), c.mz_lo);
+        out[8 * i + 7] = fin(__byte_perm(b23, MBYTES, 0x4342), c.mz_lo);
+      }
     }
   }
 }
 
-template <int BITS>
+template <int BITS, bool IL>
 __device__ __forceinline__ void dequant_half_row_i8(uint32_t src, uint32_t (&out)[16], uint32_t zp4) {
   if constexpr (BITS == 2) {
     const uint4 pk = lds128(src);
@@ -268,7 +295,17 @@ __device__ __forceinline__ void dequant_half_row_i8(uint32_t src, uint32_t (&out
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t h[4];
-      decode_u2x16_to_u8(w[i], zp4 ? 0x80808080u : 0u, h);
+      if constexpr (IL) {
+        decode_u2x16_to_u8(w[i], zp4 ? 0x80808080u : 0u, h);
+      } else {
+        const uint32_t orv = zp4 ? 0x80808080u : 0u;
+        const uint32_t s0 = lop3_and_or(w[i], 0x03030303u, orv), s1 = lop3_and_or(w[i] >> 2, 0x03030303u, orv),
+                       s2 = lop3_and_or(w[i] >> 4, 0x03030303u, orv), s3 = lop3_and_or(w[i] >> 6, 0x03030303u, orv);
+        const uint32_t a = __byte_perm(s0, s1, 0x5140), b = __byte_perm(s2, s3, 0x5140);
+        const uint32_t a2 = __byte_perm(s0, s1, 0x7362), b2 = __byte_perm(s2, s3, 0x7362);
+        h[0] = __byte_perm(a, b, 0x5410); h[1] = __byte_perm(a, b, 0x7632);
+        h[2] = __byte_perm(a2, b2, 0x5410); h[3] = __byte_perm(a2, b2, 0x7632);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) out[4 * i + j] = zp4 ? bytes_sub_zp(h[j], zp4) : h[j];
     }
@@ -279,14 +316,20 @@ __device__ __forceinline__ void dequant_half_row_i8(uint32_t src, uint32_t (&out
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       uint32_t h[2];
-      decode_u4x8_to_u8(w[i], zp4 ? 0x80808080u : 0u, h);
+      if constexpr (IL) {
+        decode_u4x8_to_u8(w[i], zp4 ? 0x80808080u : 0u, h);
+      } else {
+        const uint32_t orv = zp4 ? 0x80808080u : 0u;
+        const uint32_t t = lop3_and_or(w[i], 0x0f0f0f0fu, orv), u = lop3_and_or(w[i] >> 4, 0x0f0f0f0fu, orv);
+        h[0] = __byte_perm(t, u, 0x5140); h[1] = __byte_perm(t, u, 0x7362);
+      }
 #pragma unroll
       for (int j = 0; j < 2; ++j) out[2 * i + j] = zp4 ? bytes_sub_zp(h[j], zp4) : h[j];
     }
   }
 }
 
-template <typename T, int BITS, int BM>
+template <typename T, int BITS, int BM, bool IL>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TsParams p) {
   using SM = TsSmem<T, BITS, BM>;
@@ -384,7 +427,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t MAGIC = INT8 ? 0u : TypeTraits<typename std::conditional<INT8, __half, T>::type>::kMagic;
     using TF = typename std::conditional<INT8, __half, T>::type;  // float-ish type for the 16-bit path
 
-    constexpr bool HI = !INT8 && std::is_same<TF, __half>::value && BITS == 4;
+    constexpr bool HI = IL && !INT8 && std::is_same<TF, __half>::value && BITS == 4;
     constexpr uint32_t MAGIC_HI = HI ? 0x54005400u : MAGIC;
     constexpr int ZSH = HI ? 16 : 1;  // odd-nibble values are 64 + u: the folded zero point sits 4 mantissa bits up
     static_assert(TA_SLOTS == 2 * DQ_GROUPS && (S % DQ_GROUPS) == 0, "slot / stage ownership is static per group");
@@ -444,8 +487,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         mbar_wait(&full[st], full_par);
         uint32_t regs[16];
-        if constexpr (INT8) dequant_half_row_i8<BITS>(src0 + st * SM::kWBytes, regs, uint32_t(p.zp_const) * 0x01010101u);
-        else dequant_half_row<TF, BITS, MODE>(src0 + st * SM::kWBytes, regs, c);
+        if constexpr (INT8) dequant_half_row_i8<BITS, IL>(src0 + st * SM::kWBytes, regs, uint32_t(p.zp_const) * 0x01010101u);
+        else dequant_half_row<TF, BITS, MODE, IL>(src0 + st * SM::kWBytes, regs, c);
         // publish the PREVIOUS k-block's TMEM slot only now: its tcgen05.st had the whole decode above to land
         if (prev_slot >= 0) {
           tmem_wait_st();
@@ -576,11 +619,11 @@ int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint
   return 0;
 }
 
-template <typename T, int BITS, int BM>
+template <typename T, int BITS, int BM, bool IL>
 int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
   using SM = TsSmem<T, BITS, BM>;
   using EI = ElemInfo<T>;
-  auto kernel = gemm_ts_kernel<T, BITS, BM>;
+  auto kernel = gemm_ts_kernel<T, BITS, BM, IL>;
   static bool attr_set = false;
   if (!attr_set) {
     BB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
@@ -605,12 +648,16 @@ int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
   return 0;
 }
 
+template <typename T, int BITS, bool IL>
+int launch_ts_bm2(const MatmulArgs& a, const TsParams& p) {
+  if (a.m <= 32) return launch_ts_inst<T, BITS, 32, IL>(a, p);
+  if (a.m <= 64) return launch_ts_inst<T, BITS, 64, IL>(a, p);
+  if (a.m <= 128) return launch_ts_inst<T, BITS, 128, IL>(a, p);
+  return launch_ts_inst<T, BITS, 256, IL>(a, p);
+}
 template <typename T, int BITS>
 int launch_ts_bm(const MatmulArgs& a, const TsParams& p) {
-  if (a.m <= 32) return launch_ts_inst<T, BITS, 32>(a, p);
-  if (a.m <= 64) return launch_ts_inst<T, BITS, 64>(a, p);
-  if (a.m <= 128) return launch_ts_inst<T, BITS, 128>(a, p);
-  return launch_ts_inst<T, BITS, 256>(a, p);
+  return a.d.w_layout == BB_LAYOUT_COMPRESSED ? launch_ts_bm2<T, BITS, false>(a, p) : launch_ts_bm2<T, BITS, true>(a, p);
 }
 
 }  // namespace
@@ -622,13 +669,13 @@ bool gemm_ts_supported(const bb_matmul_desc& d, int m) {
   if (d.N % TS_ROWS) return false;
   const int g = d.group_size <= 0 ? d.K : d.group_size;
   if (d.a_dtype == BB_I8) {
-    if (d.accum_dtype != BB_I32 || d.w_layout != BB_LAYOUT_INTERLEAVED_8) return false;
+    if (d.accum_dtype != BB_I32 || d.w_layout == BB_LAYOUT_INTERLEAVED_16) return false;
     if (d.with_scaling || d.with_zeros) return false;
     if (d.K % 128) return false;
     return true;
   }
   if (d.a_dtype != BB_F16 && d.a_dtype != BB_BF16) return false;
-  if (d.w_layout != BB_LAYOUT_INTERLEAVED_16) return false;
+  if (d.w_layout == BB_LAYOUT_INTERLEAVED_8) return false;
   if (d.K % 64 || g % 64 || d.K % g) return false;
   if (d.with_zeros && !d.with_scaling) return false;
   if (d.w_fmt == BB_W_INT && d.with_zeros) return false;

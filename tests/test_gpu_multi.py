@@ -1,0 +1,49 @@
+"""Multi-GPU (NCCL) column-parallel path on real devices: needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import helpers as H
+        from bitblas_b200.parallel import ColumnParallelLinear
+        for M, chunks in ((1, None), (8, None), (640, 3)):
+            N, K, g = 512, 1024, 128
+            case = H.make_case(M, N, K, W_dtype="uint4", group_size=g, with_scaling=True, with_zeros=True,
+                               zeros_mode="quantized", with_bias=True, seed=3)
+            ref = H.oracle_output(case)
+            layer = ColumnParallelLinear(K, N, bias=True, A_dtype="float16", W_dtype="uint4", group_size=g, with_scaling=True,
+                                         with_zeros=True, zeros_mode="quantized", enable_tuning=False, pipeline_chunks=chunks).cuda()
+            stored = layer.local.bitblas_matmul.weight_transform(case["fields"].to(torch.int8))
+            layer.load_full_params(stored, case["scale"], case["zeros"], case["bias"])
+            out = layer(case["A"].cuda())
+            torch.cuda.synchronize()
+            H.assert_fp_close(out.cpu(), ref, f"column-parallel M={M} rank={rank}")
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_parallel_nccl():
+    world = min(torch.cuda.device_count(), 2)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29731, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}

@@ -72,6 +72,12 @@ GEMM_CASES = [
     dict(M=128, N=256, K=1024, W_dtype="int2", group_size=-1, with_scaling=True),
     dict(M=128, N=256, K=1024, W_dtype="uint4", A_dtype="bfloat16", out_dtype="bfloat16", fast_decoding=True, group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
     dict(M=128, N=256, K=1024, W_dtype="uint4", out_dtype="float32", accum_dtype="float32", group_size=128, with_scaling=True),
+    # plain compressed storage (fast_decoding=False; the default for bfloat16 activations, general_matmul/__init__.py:174-176)
+    dict(M=128, N=256, K=1024, W_dtype="uint4", fast_decoding=False, group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=64, N=128, K=512, W_dtype="uint2", fast_decoding=False, group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=96, N=256, K=1024, W_dtype="int4", fast_decoding=False, group_size=-1, with_scaling=True),
+    dict(M=128, N=256, K=1024, W_dtype="uint4", A_dtype="bfloat16", out_dtype="bfloat16", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=128, N=128, K=512, W_dtype="uint2", A_dtype="bfloat16", out_dtype="bfloat16", group_size=128, with_scaling=True),
 ]
 
 
@@ -94,6 +100,11 @@ W2A8_CASES = [
     dict(M=128, N=256, K=1024, W_dtype="uint2", out_dtype="int32"),
     dict(M=64, N=128, K=512, W_dtype="int4", out_dtype="int32", fast_decoding=True),
     dict(M=128, N=256, K=1024, W_dtype="int2", out_dtype="int8"),
+    # W4A8 default is the plain compressed storage (general_matmul/__init__.py:171-173)
+    dict(M=128, N=256, K=1024, W_dtype="int4", out_dtype="int32"),
+    dict(M=64, N=128, K=512, W_dtype="uint4", out_dtype="int32"),
+    dict(M=100, N=128, K=512, W_dtype="int2", out_dtype="int32", fast_decoding=False),
+    dict(M=48, N=128, K=512, W_dtype="uint2", out_dtype="int32", fast_decoding=False),
 ]
 
 
