@@ -26,7 +26,7 @@ WFMT_IDS = {"uint": BB_W_UINT, "int": BB_W_INT, "nf": BB_W_NF, "fp": BB_W_FP4, "
 ZEROS_IDS = {"original": BB_ZEROS_ORIGINAL, "rescale": BB_ZEROS_RESCALE, "quantized": BB_ZEROS_QUANTIZED}
 
 EXPORTS = [
-    "bb_init", "bb_matmul", "bb_workspace_bytes", "bb_select_kernel", "bb_kernel_name", "bb_set_kernel_override",
+    "bb_init", "bb_matmul", "bb_matmul_scatter", "bb_workspace_bytes", "bb_select_kernel", "bb_kernel_name", "bb_set_kernel_override",
     "bb_launch_count", "bb_last_error", "bb_version", "bb_compress_host", "bb_interleave_host",
     "bb_transform_weight_device", "bb_repack_gptq_qweight_device", "bb_repack_gptq_qzeros_device",
     "bb_debug_decode",
@@ -59,6 +59,8 @@ def load() -> ctypes.CDLL:
     dp = ctypes.POINTER(MatmulDesc)
     lib.bb_init.argtypes = [i32]; lib.bb_init.restype = i32
     lib.bb_matmul.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, i32, vp, sz, vp]; lib.bb_matmul.restype = i32
+    lib.bb_matmul_scatter.argtypes = [dp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), i32, i64, i64, i32, vp, sz, vp]
+    lib.bb_matmul_scatter.restype = i32
     lib.bb_workspace_bytes.argtypes = [dp, i32]; lib.bb_workspace_bytes.restype = sz
     lib.bb_select_kernel.argtypes = [dp, i32]; lib.bb_select_kernel.restype = i32
     lib.bb_kernel_name.argtypes = [i32]; lib.bb_kernel_name.restype = ctypes.c_char_p

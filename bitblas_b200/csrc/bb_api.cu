@@ -139,21 +139,33 @@ size_t bb_workspace_bytes(const bb_matmul_desc* desc, int m) {
   return 0;
 }
 
-int bb_matmul(const bb_matmul_desc* desc, const void* A, const void* W, const void* lut, const void* scale,
-              const void* zeros, const void* bias, void* C, int m, void* workspace, size_t workspace_bytes,
-              void* stream) {
+static int matmul_impl(const bb_matmul_desc* desc, const void* A, const void* W, const void* lut, const void* scale,
+                       const void* zeros, const void* bias, void* C, void* const* peer_C, int n_peers, long long ldc,
+                       long long col_offset, int m, void* workspace, size_t workspace_bytes, void* stream) {
   if (validate(desc)) return 1;
   if (m == 0) return 0;  // wrapper/tl.py:156-157
   if (m < 0) { set_error("m must be >= 0 (got %d)", m); return 1; }
-  if (!A || !W || !C) { set_error("A, W and C must be non-null"); return 1; }
+  if (!A || !W || (!C && n_peers == 0)) { set_error("A, W and C must be non-null"); return 1; }
+  if (n_peers < 0 || n_peers > BB_MAX_PEERS) { set_error("n_peers must be in [0, %d]", BB_MAX_PEERS); return 1; }
+  if (n_peers > 0) {
+    if (!peer_C) { set_error("peer_C is null"); return 1; }
+    for (int i = 0; i < n_peers; ++i) if (!peer_C[i]) { set_error("peer_C[%d] is null", i); return 1; }
+    if (col_offset < 0 || col_offset + desc->N > ldc) { set_error("column shard [%lld, %lld) exceeds ldc=%lld", col_offset, col_offset + desc->N, ldc); return 1; }
+  }
   if (desc->with_scaling && !scale) { set_error("with_scaling is set but scale is null"); return 1; }
   if (desc->with_zeros && !zeros) { set_error("with_zeros is set but zeros is null"); return 1; }
   if (desc->with_bias && !bias) { set_error("with_bias is set but bias is null"); return 1; }
   if (desc->w_fmt == BB_W_NF && !lut) { set_error("nf4 weights need the 16-entry LUT"); return 1; }
   MatmulArgs a;
   a.d = *desc; a.A = A; a.W = W; a.lut = lut; a.scale = scale; a.zeros = zeros; a.bias = bias; a.C = C; a.m = m;
+  a.n_peers = n_peers; a.ldc = n_peers ? ldc : desc->N; a.col_offset = n_peers ? col_offset : 0;
+  for (int i = 0; i < BB_MAX_PEERS; ++i) a.peer_C[i] = (i < n_peers) ? peer_C[i] : nullptr;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.stream = (cudaStream_t)stream;
   const int k = select(a.d, m);
+  if (n_peers > 0 && k == BB_KERNEL_GENERIC) {
+    set_error("the column-parallel scatter epilogue needs a fast kernel (gemv_mma / gemv_i8 / gemm_ts); this configuration dispatches to generic_simt");
+    return 1;
+  }
   switch (k) {
     case BB_KERNEL_GENERIC: return launch_generic(a);
     case BB_KERNEL_GEMV_MMA: return launch_gemv_mma(a);
@@ -163,6 +175,20 @@ int bb_matmul(const bb_matmul_desc* desc, const void* A, const void* W, const vo
   }
   set_error("kernel override %d does not support this configuration", g_override.load());
   return 1;
+}
+
+int bb_matmul(const bb_matmul_desc* desc, const void* A, const void* W, const void* lut, const void* scale,
+              const void* zeros, const void* bias, void* C, int m, void* workspace, size_t workspace_bytes,
+              void* stream) {
+  return matmul_impl(desc, A, W, lut, scale, zeros, bias, C, nullptr, 0, 0, 0, m, workspace, workspace_bytes, stream);
+}
+
+int bb_matmul_scatter(const bb_matmul_desc* desc, const void* A, const void* W, const void* lut, const void* scale,
+                      const void* zeros, const void* bias, void* const* peer_C, int n_peers, int64_t ldc,
+                      int64_t col_offset, int m, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_peers < 1) { set_error("bb_matmul_scatter needs n_peers >= 1"); return 1; }
+  return matmul_impl(desc, A, W, lut, scale, zeros, bias, nullptr, peer_C, n_peers, ldc, col_offset, m, workspace,
+                     workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -46,6 +46,11 @@ struct MatmulArgs {
   const void* bias;
   void* C;
   int m;
+  // column-parallel scatter epilogue (n_peers == 0: plain single output C with row stride N)
+  void* peer_C[BB_MAX_PEERS];
+  int n_peers;
+  long long ldc;         // row stride of the output(s) in elements
+  long long col_offset;  // first output column of this shard
   void* workspace;
   size_t workspace_bytes;
   cudaStream_t stream;
@@ -85,6 +90,27 @@ __host__ __device__ __forceinline__ int field_bitpos(int o, int bits, int layout
     pos = map[pos >> 2] * 4 + (pos & 3);
   }
   return pos;
+}
+
+// where a kernel epilogue stores C[m, n]: one local buffer, or the same element in every peer's buffer
+struct OutSpec {
+  void* ptr[BB_MAX_PEERS];
+  int n;                 // number of destination buffers (>= 1)
+  long long ld;          // row stride in elements
+  long long col0;        // column offset of this shard
+};
+inline OutSpec make_outspec(const MatmulArgs& a) {
+  OutSpec o;
+  if (a.n_peers > 0) {
+    o.n = a.n_peers;
+    for (int i = 0; i < BB_MAX_PEERS; ++i) o.ptr[i] = i < a.n_peers ? a.peer_C[i] : nullptr;
+    o.ld = a.ldc; o.col0 = a.col_offset;
+  } else {
+    o.n = 1;
+    for (int i = 0; i < BB_MAX_PEERS; ++i) o.ptr[i] = i == 0 ? a.C : nullptr;
+    o.ld = a.d.N; o.col0 = 0;
+  }
+  return o;
 }
 
 // ---- small device utilities -----------------------------------------------------------------

@@ -155,7 +155,7 @@ struct TsParams {
   const void* scale;
   const void* zeros;
   const void* bias;
-  void* C;
+  OutSpec out;
   int M, N, K;
   int g, G;
   int mode;       // 0 none, 1 scale, 2 original, 3 rescale, 4 quantized
@@ -548,29 +548,34 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = 0; c < CH; ++c) {
         const int m = m0 + c0 + c;
         if (m >= p.M) break;
-        const size_t o = size_t(m) * p.N + n;
+        const size_t o = size_t(m) * size_t(p.out.ld) + size_t(p.out.col0) + n;
+        // one store per destination buffer: the local output, or every rank's copy (peer-mapped, NVLink) when sharded
         if constexpr (INT8) {
           const int acc = int(v[c]);
           const int b = int(bias_f);
-          switch (p.out_dtype) {
-            case BB_I32: reinterpret_cast<int*>(p.C)[o] = acc + b; break;
-            case BB_I8: reinterpret_cast<int8_t*>(p.C)[o] = int8_t(int8_t(acc) + b); break;
-            case BB_F32: reinterpret_cast<float*>(p.C)[o] = float(acc) + float(b); break;
-            case BB_F16: reinterpret_cast<__half*>(p.C)[o] = __hadd(__int2half_rn(acc), __int2half_rn(b)); break;
-            default: reinterpret_cast<__nv_bfloat16*>(p.C)[o] = __hadd(__int2bfloat16_rn(acc), __int2bfloat16_rn(b));
+          for (int d = 0; d < p.out.n; ++d) {
+            void* Cd = p.out.ptr[d];
+            switch (p.out_dtype) {
+              case BB_I32: reinterpret_cast<int*>(Cd)[o] = acc + b; break;
+              case BB_I8: reinterpret_cast<int8_t*>(Cd)[o] = int8_t(int8_t(acc) + b); break;
+              case BB_F32: reinterpret_cast<float*>(Cd)[o] = float(acc) + float(b); break;
+              case BB_F16: reinterpret_cast<__half*>(Cd)[o] = __hadd(__int2half_rn(acc), __int2half_rn(b)); break;
+              default: reinterpret_cast<__nv_bfloat16*>(Cd)[o] = __hadd(__int2bfloat16_rn(acc), __int2bfloat16_rn(b));
+            }
           }
         } else {
           const float acc = __uint_as_float(v[c]);
           if (p.out_dtype == BB_F16) {
             __half h = __float2half_rn(acc);
             if (p.bias) h = __hadd(h, __float2half_rn(bias_f));
-            reinterpret_cast<__half*>(p.C)[o] = h;
+            for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__half*>(p.out.ptr[d])[o] = h;
           } else if (p.out_dtype == BB_BF16) {
             __nv_bfloat16 h = __float2bfloat16_rn(acc);
             if (p.bias) h = __hadd(h, __float2bfloat16_rn(bias_f));
-            reinterpret_cast<__nv_bfloat16*>(p.C)[o] = h;
+            for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__nv_bfloat16*>(p.out.ptr[d])[o] = h;
           } else {
-            reinterpret_cast<float*>(p.C)[o] = acc + (p.bias ? bias_f : 0.f);
+            const float f = acc + (p.bias ? bias_f : 0.f);
+            for (int d = 0; d < p.out.n; ++d) reinterpret_cast<float*>(p.out.ptr[d])[o] = f;
           }
         }
       }
@@ -698,7 +703,7 @@ int launch_gemm_ts(const MatmulArgs& a) {
   p.scale = d.with_scaling ? a.scale : nullptr;
   p.zeros = d.with_zeros ? a.zeros : nullptr;
   p.bias = d.with_bias ? a.bias : nullptr;
-  p.C = a.C; p.M = a.m; p.N = d.N; p.K = d.K; p.g = a.gsize(); p.G = a.groups();
+  p.out = make_outspec(a); p.M = a.m; p.N = d.N; p.K = d.K; p.g = a.gsize(); p.G = a.groups();
   p.mode = !d.with_scaling ? 0 : (!d.with_zeros ? 1 : 2 + d.zeros_mode);
   p.zp_const = d.w_fmt == BB_W_INT ? (1 << (d.w_bits - 1)) : 0;
   p.out_dtype = d.out_dtype; p.a_dtype = d.a_dtype; p.m_tiles = 1;

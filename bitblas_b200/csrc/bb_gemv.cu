@@ -39,7 +39,7 @@ struct GemvParams {
   const void* scale;
   const void* zeros;
   const void* bias;
-  void* C;
+  OutSpec out;
   int M, N, K;
   int g;          // group size in elements (multiple of 128, or K)
   int G;          // groups per row
@@ -133,10 +133,11 @@ __device__ __forceinline__ void split_range(int total, int parts, int idx, int& 
 //   ZK: 0 no zeros (constant zero point of the "int" formats only), 1 "original", 2 "rescale", 3 "quantized"
 //   SC: with_scaling
 // ---------------------------------------------------------------------------------------------
-//   AS: (NT == 1, M <= 4) activations are staged through shared memory with cp.async one PF-step chunk ahead and
-//       read with ld.shared.  Loads of one warp complete in order, so an L1-hit ld.global issued behind the weight
-//       prefetch would wait a full DRAM round trip every step (tools/membench.cu: +22..45 % time); ld.shared does not.
-template <typename T, int BITS, bool IL, int NT, int ZK, bool SC, bool AS>
+//   ST: (NT == 1, M <= 2, ZK in {0,3}) the CTA stages the activations A[M, K] and its 16 rows of group parameters in
+//       shared memory once, BEFORE the weight stream starts, and the main loop only issues ld.shared besides the weight
+//       prefetch.  Loads of one warp complete in order: an L1-hit ld.global issued behind the prefetch of the previous step
+//       waits a DRAM round trip every step (profiles/r1_gemv_*: long-scoreboard stalls on the first HMMA of every word).
+template <typename T, int BITS, bool IL, int NT, int ZK, bool SC, bool ST>
 __global__ void __launch_bounds__(NT == 1 ? 128 : MAX_KS * 32)
 __maxnreg__(NT == 1 ? ((ZK == 1 || ZK == 2) ? 112 : 96) : (NT == 2 ? ((ZK == 1 || ZK == 2) ? 168 : 128) : ((ZK == 1 || ZK == 2) ? 232 : 192)))
 gemv_mma_kernel(const GemvParams p) {
@@ -204,6 +205,11 @@ gemv_mma_kernel(const GemvParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) asum_g[t][j] = 0.f;
 
+  extern __shared__ __align__(16) uint8_t st_smem[];
+  const uint32_t sA_base = (uint32_t)__cvta_generic_to_shared(st_smem);
+  const uint32_t sA_row_bytes = uint32_t(p.K) * 2;
+  const uint32_t sS_base = sA_base + uint32_t(ST ? p.M : 0) * sA_row_bytes;
+  const uint32_t sZ_base = sS_base + 16u * uint32_t(p.G) * 2u;
   // per-group state
   float s_a = 1.f, s_b = 1.f, zc_a = 0.f, zc_b = 0.f;
   uint32_t dzf[4] = {0u, 0u, 0u, 0u};  // -(z - rint(z)) fragment for non-integer "original" zero points
@@ -221,6 +227,23 @@ gemv_mma_kernel(const GemvParams p) {
   // group parameters are fetched one group ahead (raw bits) so their L2 latency overlaps a whole step
   uint16_t sr_a = 0, sr_b = 0, zr_a = 0, zr_b = 0;
   auto fetch_group = [&]() {
+    if constexpr (ST) {
+      const int g2 = p.G - groups_to_fetch;  // group index being fetched
+      if (groups_to_fetch > 0) {
+        if constexpr (SC) {
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sr_a) : "r"(sS_base + (r * p.G + g2) * 2));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sr_b) : "r"(sS_base + ((r + 8) * p.G + g2) * 2));
+        }
+        if constexpr (ZK == 3) {
+          uint32_t za, zb;
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(za) : "r"(sZ_base + g2 * 8 + r / EPB));
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(zb) : "r"(sZ_base + g2 * 8 + (r + 8) / EPB));
+          zr_a = uint16_t(za); zr_b = uint16_t(zb);
+        }
+        --groups_to_fetch;
+      }
+      return;
+    }
     if (groups_to_fetch > 0) {
       if constexpr (SC) {
         sr_a = __ldg(sp_a);
@@ -302,25 +325,40 @@ gemv_mma_kernel(const GemvParams p) {
       ap[t] += 16;
     }
   };
-  // ---- AS: per-warp staging buffer [2 chunks][M][PF steps][4 x 16-byte pieces][4 q]  (256 B per step per batch row)
-  extern __shared__ __align__(16) uint8_t act_smem[];
-  const int Ms = AS ? p.M : 0;
-  const uint32_t as_base = (uint32_t)__cvta_generic_to_shared(act_smem) + warp * (2 * Ms * PF * 256);
-  const uint32_t as_read = as_base + min(r, max(Ms, 1) - 1) * (PF * 256) + q * 16;  // + chunk*Ms*PF*256 + u*256 + x*64
-  auto stage_acts = [&](int chunk_first_step, int buf) {  // steps [first, first+PF) of this warp's range
-    if constexpr (AS) {
-      const uint8_t* abytes = reinterpret_cast<const uint8_t*>(p.A) + (size_t(step_begin) + chunk_first_step) * 256;
-      for (int pid = lane; pid < Ms * PF * 16; pid += 32) {
-        const int m = pid / (PF * 16), rem = pid % (PF * 16), u = rem >> 4, pp = rem & 15;
-        if (chunk_first_step + u < ns)
-          cp_async16(as_base + ((buf * Ms + m) * PF + u) * 256 + (pp & 3) * 64 + (pp >> 2) * 16,
-                     abytes + size_t(m) * p.K * sizeof(T) + u * 256 + pp * 16);
-      }
-      cp_async_commit();
+  // ---- ST: CTA-wide staging.  sA: per batch row, per 128-k step 256 B, pieces permuted so that the four q lanes of a
+  // quad read 64 contiguous bytes per ld.shared.v4 (piece (q, x) of a step lives at x*64 + q*16); sS: scales [16][G]
+  // (raw 16-bit); sZ: quantized zero bytes [G][8]
+  if constexpr (ST) {
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    const uint4* Ag = reinterpret_cast<const uint4*>(p.A);
+    const int pieces_per_row = p.K / 8;  // 16-byte pieces
+    for (int pid = tid; pid < p.M * pieces_per_row; pid += nthr) {
+      const int m = pid / pieces_per_row, pr = pid % pieces_per_row, pp = pr & 15;
+      const uint4 v = __ldg(Ag + pid);
+      const uint32_t dst = sA_base + m * sA_row_bytes + (pr >> 4) * 256 + (pp & 3) * 64 + (pp >> 2) * 16;
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
     }
-  };
-  auto read_acts = [&](int buf, int u, uint32_t (&dst)[NT][RPS]) {
-    const uint32_t a = as_read + (buf * Ms * PF + u) * 256;
+    if constexpr (SC) {
+      const uint16_t* sg = reinterpret_cast<const uint16_t*>(p.scale) + size_t(rb) * 16 * p.G;  // 16 consecutive rows
+      for (int i = tid; i < 16 * p.G; i += nthr) {
+        const uint16_t v = __ldg(sg + i);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sS_base + i * 2), "h"(v));
+      }
+    }
+    if constexpr (ZK == 3) {
+      const uint8_t* zg = reinterpret_cast<const uint8_t*>(p.zeros) + size_t(rb) * 16 / EPB;
+      const int bpg = 16 / EPB;  // zero bytes per group for this row block
+      for (int i = tid; i < p.G * bpg; i += nthr) {
+        const int g2 = i / bpg, b = i % bpg;
+        const uint32_t v = __ldg(zg + size_t(g2) * qz_stride + b);
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(sZ_base + g2 * 8 + b), "r"(v));
+      }
+    }
+    __syncthreads();
+  }
+  const uint32_t sA_read = sA_base + min(r, max(p.M, 1) - 1) * sA_row_bytes + uint32_t(step_begin) * 256 + q * 16;
+  auto read_acts = [&](int step_local, uint32_t (&dst)[NT][RPS]) {
+    const uint32_t a = sA_read + step_local * 256;
 #pragma unroll
     for (int x = 0; x < RPS / 4; ++x)
       asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -391,32 +429,24 @@ gemv_mma_kernel(const GemvParams p) {
     }
     fetch_group();   // first group's parameters: the only synchronous fetch, overlapped with the weight prologue
     begin_group();
-    if constexpr (AS) stage_acts(0, 0);
     // GUARD = false: the chunk and all of its refills are inside the range (no per-step predicates)
     auto chunk = [&](auto guard_tag, int s, int buf) {
       constexpr bool GUARD = decltype(guard_tag)::value;
-      if constexpr (AS) {
-        stage_acts(s + PF, buf ^ 1);   // next chunk's activations: in flight for a whole chunk
-        cp_async_wait<1>();            // this chunk's activations have landed ...
-        __syncwarp();                  // ... including the pieces copied by the other lanes
-      }
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         if (!GUARD || s + u < ns) {
-          if constexpr (AS) read_acts(buf, u, Rbuf[0]); else load_acts(Rbuf[0]);
+          if constexpr (ST) read_acts(s + u, Rbuf[0]); else load_acts(Rbuf[0]);
           process(wq[u][0], wq[u][1], Rbuf[0]);
           if (!GUARD || s + u + PF < ns) { load_w<BITS>(wnext_a, wq[u][0]); load_w<BITS>(wnext_b, wq[u][1]); }
           wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
         }
       }
-      if constexpr (AS) __syncwarp();  // all lanes done reading `buf` before it is overwritten two chunks later
     };
     int s = 0, buf = 0;
 #pragma unroll 1
     for (; s + 2 * PF <= ns; s += PF, buf ^= 1) chunk(std::false_type{}, s, buf);
 #pragma unroll 1
     for (; s < ns; s += PF, buf ^= 1) chunk(std::true_type{}, s, buf);
-    if constexpr (AS) cp_async_wait<0>();
     end_group();
   }
 
@@ -435,18 +465,18 @@ gemv_mma_kernel(const GemvParams p) {
     float v = 0.f;
     for (int w = 0; w < p.ks; ++w) v += red[w][row][m];
     const int n = rb * 16 + row;
-    const size_t o = size_t(m) * p.N + n;
+    const size_t o = size_t(m) * size_t(p.out.ld) + size_t(p.out.col0) + n;
     const float bf = p.bias ? TypeTraits<T>::to_float(reinterpret_cast<const T*>(p.bias)[n]) : 0.f;
     if (p.out_dtype == BB_F16) {
       __half h = __float2half_rn(v);
       if (p.bias) h = __hadd(h, __float2half_rn(bf));
-      reinterpret_cast<__half*>(p.C)[o] = h;
+      for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__half*>(p.out.ptr[d])[o] = h;
     } else if (p.out_dtype == BB_BF16) {
       __nv_bfloat16 h = __float2bfloat16_rn(v);
       if (p.bias) h = __hadd(h, __float2bfloat16_rn(bf));
-      reinterpret_cast<__nv_bfloat16*>(p.C)[o] = h;
+      for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__nv_bfloat16*>(p.out.ptr[d])[o] = h;
     } else {
-      reinterpret_cast<float*>(p.C)[o] = v + bf;
+      for (int d = 0; d < p.out.n; ++d) reinterpret_cast<float*>(p.out.ptr[d])[o] = v + bf;
     }
   }
 }
@@ -561,13 +591,16 @@ gemv_i8_kernel(const GemvParams p) {
     for (int w = 0; w < p.ks; ++w) v += red[w][row][m];
     const int n = rb * 16 + row;
     const int b = p.bias ? int(reinterpret_cast<const int8_t*>(p.bias)[n]) : 0;
-    const size_t o = size_t(m) * p.N + n;
-    switch (p.out_dtype) {
-      case BB_I32: reinterpret_cast<int*>(p.C)[o] = v + b; break;
-      case BB_I8: reinterpret_cast<int8_t*>(p.C)[o] = int8_t(int8_t(v) + b); break;
-      case BB_F32: reinterpret_cast<float*>(p.C)[o] = float(v) + float(b); break;
-      case BB_F16: reinterpret_cast<__half*>(p.C)[o] = __hadd(__int2half_rn(v), __int2half_rn(b)); break;
-      default: reinterpret_cast<__nv_bfloat16*>(p.C)[o] = __hadd(__int2bfloat16_rn(v), __int2bfloat16_rn(b));
+    const size_t o = size_t(m) * size_t(p.out.ld) + size_t(p.out.col0) + n;
+    for (int d = 0; d < p.out.n; ++d) {
+      void* Cd = p.out.ptr[d];
+      switch (p.out_dtype) {
+        case BB_I32: reinterpret_cast<int*>(Cd)[o] = v + b; break;
+        case BB_I8: reinterpret_cast<int8_t*>(Cd)[o] = int8_t(int8_t(v) + b); break;
+        case BB_F32: reinterpret_cast<float*>(Cd)[o] = float(v) + float(b); break;
+        case BB_F16: reinterpret_cast<__half*>(Cd)[o] = __hadd(__int2half_rn(v), __int2half_rn(b)); break;
+        default: reinterpret_cast<__nv_bfloat16*>(Cd)[o] = __hadd(__int2bfloat16_rn(v), __int2bfloat16_rn(b));
+      }
     }
   }
 }
@@ -576,7 +609,7 @@ GemvParams make_params(const MatmulArgs& a) {
   GemvParams p;
   const bb_matmul_desc& d = a.d;
   p.A = a.A; p.W = (const uint8_t*)a.W; p.scale = d.with_scaling ? a.scale : nullptr;
-  p.zeros = d.with_zeros ? a.zeros : nullptr; p.bias = d.with_bias ? a.bias : nullptr; p.C = a.C;
+  p.zeros = d.with_zeros ? a.zeros : nullptr; p.bias = d.with_bias ? a.bias : nullptr; p.out = make_outspec(a);
   p.M = a.m; p.N = d.N; p.K = d.K;
   p.g = a.gsize(); p.G = a.groups();
   p.with_scaling = d.with_scaling;
@@ -596,7 +629,7 @@ int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_bl
     if (ks > steps) continue;
     if (occ_cache[ks] < 0) {
       int occ = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, ks * 32, size_t(ks) * stage_bytes) != cudaSuccess) occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, ks * 32, size_t(stage_bytes)) != cudaSuccess) occ = 0;
       occ_cache[ks] = occ;
     }
     if (row_blocks <= sms * occ_cache[ks]) return ks;
@@ -609,21 +642,23 @@ int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_bl
     static int occ_cache_store[5][MAX_KS + 1];                                 \
     static bool occ_init = false;                                              \
     if (!occ_init) { for (auto& row : occ_cache_store) for (int& v : row) v = -1; occ_init = true; } \
-    int (&occ_cache)[MAX_KS + 1] = occ_cache_store[stage_bytes ? (p.M <= 4 ? p.M : 0) : 0]; \
+    if (stage_bytes) for (int& v : occ_cache_store[1]) v = -1;  /* staged: smem depends on K -> recompute */ \
+    int (&occ_cache)[MAX_KS + 1] = occ_cache_store[stage_bytes ? 1 : 0];       \
     p.ks = pick_ks(KERNEL, occ_cache, MAXKS, nb, p.K / 128, stage_bytes);      \
-    KERNEL<<<nb, p.ks * 32, p.ks * stage_bytes, a.stream>>>(p);                \
+    KERNEL<<<nb, p.ks * 32, stage_bytes, a.stream>>>(p);                       \
   }
 
 template <typename T, int BITS, bool IL>
 int launch_mma_nt(const MatmulArgs& a, GemvParams p) {
-  static const bool as_env = [] { const char* e = getenv("BB_GEMV_AS"); return e ? atoi(e) != 0 : false; }();
-  const bool pp = as_env && p.M <= 4;             // activation staging through shared memory
   const int nb = p.N / 16;
-  const int stage_bytes = pp ? 2 * p.M * PF * 256 : 0;  // per warp
   const int nt = (p.M + 7) / 8;
+  // The CTA-staged variant (ST = true: activations + group parameters in shared memory before the weight stream starts) is
+  // kept in the kernel source but not instantiated: on B200 it measured SLOWER than loading the activations with
+  // ld.global at use (12288^2, m=1: 39.2 us vs 30.7 us; 4-shape step 157 us vs 133 us) -- the staging prologue and the
+  // shared-memory footprint cost more than the in-order load stalls they remove.
+  const int stage_bytes = 0;
 #define BB_GEMV_NT(ZKV, SCV)                                                             \
-  if (nt <= 1 && pp) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV, SCV, true>), 4)    \
-  else if (nt <= 1) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV, SCV, false>), 4) \
+  if (nt <= 1) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV, SCV, false>), 4) \
   else if (nt == 2) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 2, ZKV, SCV, false>), MAX_KS) \
   else BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 4, ZKV, SCV, false>), MAX_KS)
   if (!p.with_scaling) { BB_GEMV_NT(0, false) }

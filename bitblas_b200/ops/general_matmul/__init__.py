@@ -388,6 +388,35 @@ class Matmul(Operator):
             raise RuntimeError(f"bb_matmul failed (code {rc}): {_lib.last_error()}")
         return output
 
+    def forward_scatter(self, A, W, scale=None, zeros=None, bias=None, *, peer_ptrs, ldc: int, col_offset: int):
+        """Column-parallel forward (bb_matmul_scatter): this operator's N is the local shard; the kernel epilogue stores the
+        [m, N] result into columns [col_offset, col_offset+N) of every buffer in `peer_ptrs` (device pointers of the
+        ranks' [m, ldc] outputs, e.g. torch symmetric memory).  Returns nothing: the caller barriers, then reads."""
+        if self.consistent:
+            raise NotImplementedError("forward_scatter needs a low-bit weight operator")
+        c = self.config
+        adt = getattr(torch, c.A_dtype)
+        self._check_tensor(A, "A", adt)
+        if A.shape[-1] != c.K:
+            raise ValueError(f"A has inner dimension {A.shape[-1]}, expected K={c.K}")
+        m = reduce(_operator.mul, A.shape[:-1], 1)
+        n = len(peer_ptrs)
+        arr = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(x)) for x in peer_ptrs])
+        dev = A.device.index if A.device.index is not None else torch.cuda.current_device()
+        _lib.ensure_init(dev)
+        stream = torch.cuda.current_stream(device=A.device).cuda_stream
+        lut = self.lut
+        if lut is not None and lut.device != A.device:
+            lut = self.lut = lut.to(A.device)
+        rc = self.lib._c.bb_matmul_scatter(ctypes.byref(self._desc), A.data_ptr(), W.data_ptr(),
+                                           lut.data_ptr() if lut is not None else 0,
+                                           scale.data_ptr() if c.with_scaling else 0,
+                                           zeros.data_ptr() if c.with_zeros else 0,
+                                           bias.data_ptr() if c.with_bias else 0,
+                                           arr, n, int(ldc), int(col_offset), int(m), 0, 0, stream)
+        if rc != 0:
+            raise RuntimeError(f"bb_matmul_scatter failed (code {rc}): {_lib.last_error()}")
+
     def _forward_consistent(self, A, W, bias, output):
         # A_dtype == W_dtype (no sub-byte decode): outside the hot path (SURVEY.md §8f-3); library GEMM.
         if not A.is_cuda:

@@ -54,8 +54,13 @@ class ColumnParallelLinear(nn.Module):
     """y = gather_N( x @ dequant(W_r)^T (+ b_r) ) with W sharded by rows (output features) across the group."""
 
     def __init__(self, in_features: int, out_features: int, *, process_group=None, gather_output: bool = True,
-                 pipeline_chunks: Optional[int] = None, **linear_kwargs):
+                 pipeline_chunks: Optional[int] = None, fused_gather: Optional[bool] = None, **linear_kwargs):
         super().__init__()
+        # fused_gather: the matmul kernel's epilogue stores this rank's column slice straight into every rank's output
+        # (peer-mapped symmetric memory over NVLink/NVSwitch) -- no separate collective, the transfer overlaps the math
+        # tile by tile.  None = use it when torch symmetric memory is available on CUDA, else NCCL all-gather.
+        self.fused_gather = fused_gather
+        self._symm = {}       # (rows capacity, dtype) -> [two (tensor, handle) pairs, next index]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
@@ -88,9 +93,53 @@ class ColumnParallelLinear(nn.Module):
             return max(1, min(self.pipeline_chunks, m))
         return max(1, min(8, m // 512))
 
+    def _symm_buffers(self, m: int, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        cap = 1
+        while cap < m:
+            cap *= 2
+        key = (cap, dtype)
+        if key not in self._symm:
+            pairs = []
+            for _ in range(2):  # double buffered: one barrier per call is enough (see forward)
+                t = symm_mem.empty((cap, self.out_features), dtype=dtype, device=device)
+                h = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+                pairs.append((t, h))
+            self._symm[key] = [pairs, 0]
+        entry = self._symm[key]
+        t, h = entry[0][entry[1]]
+        entry[1] ^= 1
+        return t, h
+
+    def _forward_fused(self, x2: torch.Tensor) -> torch.Tensor:
+        m = x2.shape[0]
+        op = self.local.bitblas_matmul
+        out_dtype = getattr(torch, op.out_dtype)
+        buf, hdl = self._symm_buffers(m, out_dtype, x2.device)
+        lin = self.local
+        op.forward_scatter(x2.contiguous(), lin.qweight, scale=lin.scales if op.with_scaling else None,
+                           zeros=lin.zeros if op.with_zeros else None, bias=lin.bias if op.with_bias else None,
+                           peer_ptrs=[int(p) for p in hdl.buffer_ptrs], ldc=self.out_features, col_offset=self.n_lo)
+        # every rank's slice has landed in every buffer once all ranks passed this point.  Buffers alternate between calls:
+        # a rank can only overwrite buffer b again after the NEXT call's barrier, which every peer reaches after its
+        # (stream-ordered) reads of this call's result.
+        hdl.barrier(channel=0)
+        return buf[:m]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.world == 1 or not self.gather_output:
             return self.local(x)
+        if x.is_cuda and self.fused_gather is not False and not self.local.consistent:
+            try:
+                out = self._forward_fused(x.reshape(-1, x.shape[-1]))
+                self.fused_gather = True
+                return out.reshape(*x.shape[:-1], self.out_features)
+            except Exception as e:  # symmetric memory unavailable / kernel family without a scatter epilogue
+                if self.fused_gather is True:
+                    raise
+                import logging
+                logging.getLogger(__name__).warning("fused column-parallel gather unavailable (%s); using NCCL all-gather", e)
+                self.fused_gather = False
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         m = x2.shape[0]

@@ -105,6 +105,17 @@ int bb_matmul(const bb_matmul_desc* desc, const void* A, const void* W, const vo
               const void* zeros, const void* bias, void* C, int m, void* workspace, size_t workspace_bytes,
               void* stream);
 
+/* Column-parallel variant (no reference counterpart: the reference is single-GPU).  `desc->N` is THIS
+ * rank's shard of the output features; the epilogue of the matmul kernel stores the [m, desc->N] result into columns
+ * [col_offset, col_offset + desc->N) of EVERY buffer in `peer_C` (row stride `ldc` elements) -- the peers' copies are
+ * peer-mapped device pointers (NVLink P2P / symmetric memory), so the all-gather of the sharded outputs happens inside the
+ * kernel, tile by tile, instead of as a separate collective.  The caller must barrier across ranks before reading.
+ * n_peers <= BB_MAX_PEERS. */
+#define BB_MAX_PEERS 8
+int bb_matmul_scatter(const bb_matmul_desc* desc, const void* A, const void* W, const void* lut, const void* scale,
+                      const void* zeros, const void* bias, void* const* peer_C, int n_peers, int64_t ldc,
+                      int64_t col_offset, int m, void* workspace, size_t workspace_bytes, void* stream);
+
 /* scratch (fp32 split-K partials) the chosen kernel needs for this (desc, m); 0 for most configs. */
 size_t bb_workspace_bytes(const bb_matmul_desc* desc, int m);
 

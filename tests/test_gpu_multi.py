@@ -33,6 +33,19 @@ def _worker(rank, world, port, ret):
             out = layer(case["A"].cuda())
             torch.cuda.synchronize()
             H.assert_fp_close(out.cpu(), ref, f"column-parallel M={M} rank={rank}")
+            fused_ok = layer.fused_gather is True
+            # NCCL all-gather path on the same inputs must agree bit for bit with the fused peer-store epilogue
+            layer.fused_gather = False
+            out2 = layer(case["A"].cuda())
+            torch.cuda.synchronize()
+            assert torch.equal(out2.cpu(), out.cpu()), f"fused vs NCCL mismatch M={M}"
+            # several calls in a row exercise the double buffering
+            layer.fused_gather = None
+            for _ in range(3):
+                out3 = layer(case["A"].cuda())
+            torch.cuda.synchronize()
+            assert torch.equal(out3.cpu(), out.cpu())
+            ret[f"fused{rank}_{M}"] = fused_ok
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -46,4 +59,6 @@ def test_column_parallel_nccl():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, 29731, ret), nprocs=world, join=True)
-    assert dict(ret) == {0: "ok", 1: "ok"}
+    d = dict(ret)
+    assert d[0] == "ok" and d[1] == "ok", d
+    print("fused gather used:", {k: v for k, v in d.items() if str(k).startswith("fused")})
