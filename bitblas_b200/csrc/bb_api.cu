@@ -3,8 +3,8 @@
 // Dispatch mirrors the reference's run-time choice (bitblas/ops/general_matmul/tilelang/dequantize/
 // matmul_dequantize.py:93-111: M < 8 -> SIMT GEMV, else MMA GEMM; and the per-opt_M if-chain emitted into
 // `call`, bitblas/builder/wrapper/tl.py:278-300) but is keyed on the B200 regimes instead:
-//   m <= 32  : memory-bound streaming kernels (bb_gemv.cu)
-//   m  > 32  : tcgen05 tensor-core kernel (bb_gemm_ts.cu)
+//   m <= 8   : memory-bound streaming kernels (bb_gemv.cu)
+//   m  > 8   : tcgen05 tensor-core kernel (bb_gemm_ts.cu), split-K when the tile grid is smaller than the chip
 //   anything the fast kernels do not cover: the generic SIMT kernel (bb_generic.cu).
 #include <cstring>
 #include <mutex>
@@ -76,11 +76,17 @@ static int select(const bb_matmul_desc& d, int m) {
     }
     return -1;
   }
-  if (m <= 32) {
+  // m <= 8 (one n8 MMA tile): streaming kernels; above that the tcgen05 kernel (split-K keeps the SMs busy at small m)
+  // is faster (12288^2 sweep, tools/smallm_sweep.py); the streaming kernels stay as the fallback up to m = 32.
+  if (m <= 8) {
     if (gemv_mma_supported(d, m)) return BB_KERNEL_GEMV_MMA;
     if (gemv_i8_supported(d, m)) return BB_KERNEL_GEMV_I8;
   }
   if (gemm_ts_supported(d, m)) return d.a_dtype == BB_I8 ? BB_KERNEL_GEMM_TS_I8 : BB_KERNEL_GEMM_TS;
+  if (m <= 32) {
+    if (gemv_mma_supported(d, m)) return BB_KERNEL_GEMV_MMA;
+    if (gemv_i8_supported(d, m)) return BB_KERNEL_GEMV_I8;
+  }
   return BB_KERNEL_GENERIC;
 }
 

@@ -21,6 +21,7 @@
 // the 128 B/clk/SM shared-memory budget at full tensor rate.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "bb_common.cuh"
@@ -163,6 +164,10 @@ struct TsParams {
   int out_dtype;
   int a_dtype;
   int m_tiles;
+  int stages;        // smem pipeline depth (even; <= TsSmem::kStages)
+  int splits;        // split-K factor (>1: fp32 / int32 partials go to `ws`, reduced by splitk_reduce_kernel)
+  int kb_per_split;  // k-blocks per split
+  void* ws;          // [splits][M][N] partials
 };
 
 template <typename T>
@@ -330,11 +335,11 @@ __device__ __forceinline__ void dequant_half_row_i8(uint32_t src, uint32_t (&out
 }
 
 template <typename T, int BITS, int BM, bool IL>
-__global__ void __launch_bounds__(TS_THREADS, 1)
+__global__ void __launch_bounds__(TS_THREADS, BM <= 128 ? 2 : 1)
 gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TsParams p) {
   using SM = TsSmem<T, BITS, BM>;
   using EI = ElemInfo<T>;
-  constexpr int S = SM::kStages;
+  const int S = p.stages;
   constexpr int KB = EI::kKB;
   constexpr int PRB = SM::kPRB;
   constexpr bool INT8 = EI::kInt8;
@@ -354,10 +359,13 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x % p.m_tiles;
-  const int n_tile = blockIdx.x / p.m_tiles;
+  const int split = blockIdx.x % p.splits;
+  const int tile = blockIdx.x / p.splits;
+  const int m_tile = tile % p.m_tiles;
+  const int n_tile = tile / p.m_tiles;
+  const int kb0 = split * p.kb_per_split;  // first k-block of this CTA
   const int m0 = m_tile * BM, n0 = n_tile * TS_ROWS;
-  const int num_kb = p.K / KB;
+  const int num_kb = p.kb_per_split;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -381,8 +389,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < num_kb; ++kb) {
         if (kb >= S) mbar_wait(&empty[s], par);
         mbar_arrive_expect_tx(&full[s], SM::kStageBytes);
-        tma_load_2d(sA + s * SM::kActBytes, &tmA, kb * KB, m0, &full[s]);
-        tma_load_2d(sW + s * SM::kWBytes, &tmW, kb * PRB, n0, &full[s]);
+        tma_load_2d(sA + s * SM::kActBytes, &tmA, (kb0 + kb) * KB, m0, &full[s]);
+        tma_load_2d(sW + s * SM::kWBytes, &tmW, (kb0 + kb) * PRB, n0, &full[s]);
         if (++s == S) { s = 0; par ^= 1; }
       }
     }
@@ -430,7 +438,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr bool HI = IL && !INT8 && std::is_same<TF, __half>::value && BITS == 4;
     constexpr uint32_t MAGIC_HI = HI ? 0x54005400u : MAGIC;
     constexpr int ZSH = HI ? 16 : 1;  // odd-nibble values are 64 + u: the folded zero point sits 4 mantissa bits up
-    static_assert(TA_SLOTS == 2 * DQ_GROUPS && (S % DQ_GROUPS) == 0, "slot / stage ownership is static per group");
+    static_assert(TA_SLOTS == 2 * DQ_GROUPS, "slot ownership is static per group");
     const int kb_per_g = p.g / KB;
     const uint16_t* sc_row = reinterpret_cast<const uint16_t*>(p.scale) + size_t(n) * p.G;
     const uint16_t* z_row = reinterpret_cast<const uint16_t*>(p.zeros) + size_t(n) * p.G;
@@ -455,8 +463,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (MODE == 2 || MODE == 3) z_raw = __ldg(z_row + gi);
         if constexpr (MODE == 4) qz_raw = __ldg(qz_col + size_t(gi) * qz_stride);
       };
-      int gi = grp / kb_per_g;           // group of this warp's first k-block
-      int g_end = (gi + 1) * kb_per_g;   // first k-block of the next group
+      int gi = (kb0 + grp) / kb_per_g;         // group of this warp's first k-block
+      int g_end = (gi + 1) * kb_per_g - kb0;   // first (CTA-local) k-block of the next group
       const int g_step = kb_per_g >= DQ_GROUPS ? 1 : DQ_GROUPS / kb_per_g;  // groups skipped per switch
       bool fresh = true;
       if constexpr (MODE != 0) fetch_group(gi);
@@ -548,6 +556,10 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = 0; c < CH; ++c) {
         const int m = m0 + c0 + c;
         if (m >= p.M) break;
+        if (p.splits > 1) {  // raw partial accumulator; bias / cast / scatter happen in splitk_reduce_kernel
+          reinterpret_cast<uint32_t*>(p.ws)[(size_t(split) * p.M + m) * p.N + n] = v[c];
+          continue;
+        }
         const size_t o = size_t(m) * size_t(p.out.ld) + size_t(p.out.col0) + n;
         // one store per destination buffer: the local output, or every rank's copy (peer-mapped, NVLink) when sharded
         if constexpr (INT8) {
@@ -588,6 +600,63 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc<NCOLS>(tmem_base);
   }
+}
+
+// out[m, n] = cast(sum_s ws[s][m][n]) (+ bias), stored to every destination of the OutSpec
+template <bool INT8>
+__global__ void splitk_reduce_kernel(const TsParams p) {
+  const size_t total = size_t(p.M) * p.N;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int m = int(i / p.N), n = int(i % p.N);
+    const size_t o = size_t(m) * size_t(p.out.ld) + size_t(p.out.col0) + n;
+    float bias_f = 0.f;
+    if (p.bias) {
+      if (p.a_dtype == BB_F16) bias_f = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+      else if (p.a_dtype == BB_BF16) bias_f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+      else bias_f = float(reinterpret_cast<const int8_t*>(p.bias)[n]);
+    }
+    if constexpr (INT8) {
+      int acc = 0;
+      for (int sp = 0; sp < p.splits; ++sp) acc += reinterpret_cast<const int*>(p.ws)[size_t(sp) * total + i];
+      const int b = int(bias_f);
+      for (int d = 0; d < p.out.n; ++d) {
+        void* Cd = p.out.ptr[d];
+        switch (p.out_dtype) {
+          case BB_I32: reinterpret_cast<int*>(Cd)[o] = acc + b; break;
+          case BB_I8: reinterpret_cast<int8_t*>(Cd)[o] = int8_t(int8_t(acc) + b); break;
+          case BB_F32: reinterpret_cast<float*>(Cd)[o] = float(acc) + float(b); break;
+          case BB_F16: reinterpret_cast<__half*>(Cd)[o] = __hadd(__int2half_rn(acc), __int2half_rn(b)); break;
+          default: reinterpret_cast<__nv_bfloat16*>(Cd)[o] = __hadd(__int2bfloat16_rn(acc), __int2bfloat16_rn(b));
+        }
+      }
+    } else {
+      float acc = 0.f;
+      for (int sp = 0; sp < p.splits; ++sp) acc += reinterpret_cast<const float*>(p.ws)[size_t(sp) * total + i];
+      if (p.out_dtype == BB_F16) {
+        __half h = __float2half_rn(acc);
+        if (p.bias) h = __hadd(h, __float2half_rn(bias_f));
+        for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__half*>(p.out.ptr[d])[o] = h;
+      } else if (p.out_dtype == BB_BF16) {
+        __nv_bfloat16 h = __float2bfloat16_rn(acc);
+        if (p.bias) h = __hadd(h, __float2bfloat16_rn(bias_f));
+        for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__nv_bfloat16*>(p.out.ptr[d])[o] = h;
+      } else {
+        const float f = acc + (p.bias ? bias_f : 0.f);
+        for (int d = 0; d < p.out.n; ++d) reinterpret_cast<float*>(p.out.ptr[d])[o] = f;
+      }
+    }
+  }
+}
+
+// split-K factor: only when the tile grid leaves most SMs idle; the k-range must split on k-block boundaries
+int choose_splits(int tiles, int num_kb, int sms) {
+  if (tiles >= sms) return 1;
+  int best = 1;
+  for (int sp = 2; sp <= 8; ++sp) {
+    if (num_kb % sp || num_kb / sp < 8) continue;
+    if (tiles * sp <= 2 * sms) best = sp;  // two CTAs per SM are resident for BM <= 128
+  }
+  return best;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -636,6 +705,22 @@ int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
   }
   TsParams p = p0;
   p.m_tiles = (a.m + BM - 1) / BM;
+  const int num_kb_total = a.d.K / EI::kKB;
+  const int tiles = p.m_tiles * (a.d.N / TS_ROWS);
+  p.splits = BM <= 128 ? choose_splits(tiles, num_kb_total, device_sm_count()) : 1;
+  if (p.splits > 1 && a.workspace_bytes < size_t(p.splits) * a.m * a.d.N * 4) p.splits = 1;  // no scratch given
+  p.kb_per_split = num_kb_total / p.splits;
+  p.ws = a.workspace;
+  // two CTAs per SM when the kernel is split (or simply small): cap the pipeline so that 2 x smem fits
+  int stages = SM::kStages;
+  if (BM <= 128 && tiles * p.splits > device_sm_count()) {
+    // more CTAs than SMs: keep the pipeline shallow enough for two resident CTAs (their windows add up); with at most
+    // one CTA per SM the full depth is needed to cover the TMA latency
+    const int cap = ((110 * 1024 - SM::kBarBytes - 1024) / SM::kStageBytes) & ~1;
+    if (cap >= 2 && cap < stages) stages = cap;
+  }
+  p.stages = stages;
+  const size_t smem_bytes = size_t(stages) * SM::kStageBytes + SM::kBarBytes + 1024;
   CUtensorMap tmA, tmW;
   const CUtensorMapDataType adt = EI::kInt8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                             : (std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -647,9 +732,17 @@ int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
   rc = make_map_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, wrow, uint64_t(a.d.N), wrow, SM::kPRB, TS_ROWS,
                    CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  const int grid = p.m_tiles * (a.d.N / TS_ROWS);
-  kernel<<<grid, TS_THREADS, SM::kTotal, a.stream>>>(tmA, tmW, p);
+  const int grid = tiles * p.splits;
+  kernel<<<grid, TS_THREADS, smem_bytes, a.stream>>>(tmA, tmW, p);
   BB_LAUNCH_CHECK();
+  if (p.splits > 1) {
+    const size_t total = size_t(a.m) * a.d.N;
+    const int rthreads = 256;
+    const int rblocks = int(std::min<size_t>((total + rthreads - 1) / rthreads, size_t(device_sm_count()) * 8));
+    if (EI::kInt8) splitk_reduce_kernel<true><<<rblocks, rthreads, 0, a.stream>>>(p);
+    else splitk_reduce_kernel<false><<<rblocks, rthreads, 0, a.stream>>>(p);
+    BB_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -689,7 +782,14 @@ bool gemm_ts_supported(const bb_matmul_desc& d, int m) {
   return true;
 }
 
-size_t gemm_ts_workspace_bytes(const bb_matmul_desc&, int) { return 0; }
+size_t gemm_ts_workspace_bytes(const bb_matmul_desc& d, int m) {
+  if (m > 128) return 0;
+  const int kb = d.a_dtype == BB_I8 ? 128 : 64;
+  const int bm = m <= 32 ? 32 : (m <= 64 ? 64 : 128);
+  const int tiles = ((m + bm - 1) / bm) * (d.N / TS_ROWS);
+  const int sp = choose_splits(tiles, d.K / kb, device_sm_count());
+  return sp > 1 ? size_t(sp) * m * d.N * 4 : 0;
+}
 
 int gemm_ts_init(int) { return get_encode() ? 0 : 0; }
 

@@ -202,7 +202,8 @@ class _LibShim:
         zeros = next(it) if op.with_zeros else 0
         bias = next(it) if op.with_bias else 0
         C = next(it)
-        rc = self._c.bb_matmul(ctypes.byref(op._desc), A, W, lut, scale, zeros, bias, C, m, 0, 0, stream)
+        ws_ptr, ws_bytes = op._workspace_for(m, torch.device("cuda", torch.cuda.current_device())) if torch.cuda.is_available() else (0, 0)
+        rc = self._c.bb_matmul(ctypes.byref(op._desc), A, W, lut, scale, zeros, bias, C, m, ws_ptr, ws_bytes, stream)
         if rc != 0:
             raise RuntimeError(f"bb_matmul failed (code {rc}): {_lib.last_error()}")
 
@@ -248,6 +249,7 @@ class Matmul(Operator):
             if torch.cuda.is_available():
                 self.lut = self.lut.cuda()
         self._desc = None
+        self._ws = {}
         self.weight_executors = None
         self.input_executors = None
         if not self.consistent:
@@ -378,15 +380,28 @@ class Matmul(Operator):
         lut = self.lut
         if lut is not None and lut.device != A.device:
             lut = self.lut = lut.to(A.device)
+        ws_ptr, ws_bytes = self._workspace_for(int(m), A.device)
         rc = self.lib._c.bb_matmul(ctypes.byref(self._desc), A.data_ptr(), W.data_ptr(),
                                    lut.data_ptr() if lut is not None else 0,
                                    scale.data_ptr() if c.with_scaling else 0,
                                    zeros.data_ptr() if c.with_zeros else 0,
                                    bias.data_ptr() if c.with_bias else 0,
-                                   output.data_ptr(), int(m), 0, 0, stream)
+                                   output.data_ptr(), int(m), ws_ptr, ws_bytes, stream)
         if rc != 0:
             raise RuntimeError(f"bb_matmul failed (code {rc}): {_lib.last_error()}")
         return output
+
+    def _workspace_for(self, m: int, device):
+        """scratch for split-K partials (bb_workspace_bytes); one cached buffer per operator and device, grown on demand.
+        Stream-ordered reuse: the reduce kernel of call i reads it before the matmul of call i+1 (same stream) writes it."""
+        need = int(self.lib._c.bb_workspace_bytes(ctypes.byref(self._desc), int(m)))
+        if need == 0:
+            return 0, 0
+        ws = self._ws.get(device)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._ws[device] = ws
+        return ws.data_ptr(), ws.numel()
 
     def forward_scatter(self, A, W, scale=None, zeros=None, bias=None, *, peer_ptrs, ldc: int, col_offset: int):
         """Column-parallel forward (bb_matmul_scatter): this operator's N is the local shard; the kernel epilogue stores the
@@ -413,7 +428,7 @@ class Matmul(Operator):
                                            scale.data_ptr() if c.with_scaling else 0,
                                            zeros.data_ptr() if c.with_zeros else 0,
                                            bias.data_ptr() if c.with_bias else 0,
-                                           arr, n, int(ldc), int(col_offset), int(m), 0, 0, stream)
+                                           arr, n, int(ldc), int(col_offset), int(m), *self._workspace_for(int(m), A.device), stream)
         if rc != 0:
             raise RuntimeError(f"bb_matmul_scatter failed (code {rc}): {_lib.last_error()}")
 

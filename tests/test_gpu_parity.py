@@ -8,11 +8,20 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def _run(case, expect_kernel=None):
+def _run(case, expect_kernel=None, force=None):
+    """force: kernel family id to pin with bb_set_kernel_override (the dispatcher prefers the tcgen05 kernel above m = 8,
+    the streaming kernels still cover m <= 32 and are tested there through the override)."""
+    from bitblas_b200 import _lib
     op = H.product_operator(case)
-    if expect_kernel is not None:
-        assert op.kernel_for(case["M"]) == expect_kernel, (op.kernel_for(case["M"]), expect_kernel)
-    got = H.run_product(op, case)
+    lib = _lib.load()
+    prev = lib.bb_set_kernel_override(force) if force is not None else None
+    try:
+        if expect_kernel is not None:
+            assert op.kernel_for(case["M"]) == expect_kernel, (op.kernel_for(case["M"]), expect_kernel)
+        got = H.run_product(op, case)
+    finally:
+        if force is not None:
+            lib.bb_set_kernel_override(prev)
     ref = H.oracle_output(case, fast_decoding=bool(op.fast_decoding))
     return op, got, ref
 
@@ -49,7 +58,8 @@ GEMV_CASES = [
 def test_gemv_mma_parity(kw):
     kw = dict(kw)
     case = H.make_case(kw.pop("M"), kw.pop("N"), kw.pop("K"), **kw)
-    op, got, ref = _run(case, "gemv_mma")
+    from bitblas_b200 import _lib
+    op, got, ref = _run(case, "gemv_mma", force=_lib.BB_KERNEL_GEMV_MMA)
     H.assert_fp_close(got, ref, "gemv_mma")
 
 
@@ -72,6 +82,13 @@ GEMM_CASES = [
     dict(M=128, N=256, K=1024, W_dtype="int2", group_size=-1, with_scaling=True),
     dict(M=128, N=256, K=1024, W_dtype="uint4", A_dtype="bfloat16", out_dtype="bfloat16", fast_decoding=True, group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
     dict(M=128, N=256, K=1024, W_dtype="uint4", out_dtype="float32", accum_dtype="float32", group_size=128, with_scaling=True),
+    dict(M=9, N=256, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=16, N=128, K=2048, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original", with_bias=True),
+    dict(M=32, N=256, K=1024, W_dtype="uint2", group_size=128, with_scaling=True),
+    # split-K (few output tiles, long K): fp32 partials in the workspace + reduce kernel
+    dict(M=64, N=128, K=4096, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized", with_bias=True),
+    dict(M=40, N=256, K=8192, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=128, N=128, K=2048, W_dtype="uint2", group_size=64, with_scaling=True),
     # plain compressed storage (fast_decoding=False; the default for bfloat16 activations, general_matmul/__init__.py:174-176)
     dict(M=128, N=256, K=1024, W_dtype="uint4", fast_decoding=False, group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
     dict(M=64, N=128, K=512, W_dtype="uint2", fast_decoding=False, group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
@@ -100,6 +117,8 @@ W2A8_CASES = [
     dict(M=128, N=256, K=1024, W_dtype="uint2", out_dtype="int32"),
     dict(M=64, N=128, K=512, W_dtype="int4", out_dtype="int32", fast_decoding=True),
     dict(M=128, N=256, K=1024, W_dtype="int2", out_dtype="int8"),
+    dict(M=64, N=128, K=4096, W_dtype="int2", out_dtype="int32"),     # split-K, int32 partials
+    dict(M=128, N=256, K=8192, W_dtype="int2", out_dtype="float32"),
     # W4A8 default is the plain compressed storage (general_matmul/__init__.py:171-173)
     dict(M=128, N=256, K=1024, W_dtype="int4", out_dtype="int32"),
     dict(M=64, N=128, K=512, W_dtype="uint4", out_dtype="int32"),
@@ -113,7 +132,12 @@ def test_int8_activation_bit_exact(kw):
     kw = dict(kw)
     M = kw["M"]
     case = H.make_case(kw.pop("M"), kw.pop("N"), kw.pop("K"), A_dtype="int8", accum_dtype="int32", **kw)
-    op, got, ref = _run(case, "gemv_i8" if M <= 32 else "gemm_ts_tcgen05_i8")
+    from bitblas_b200 import _lib
+    il8 = case["cfg"]["fast_decoding"] is not False and not (case["cfg"]["W_dtype"] in ("int4", "uint4") and case["cfg"]["fast_decoding"] is None)
+    if M <= 32 and il8:
+        op, got, ref = _run(case, "gemv_i8", force=_lib.BB_KERNEL_GEMV_I8)
+    else:
+        op, got, ref = _run(case, "gemm_ts_tcgen05_i8")
     assert torch.equal(got, ref)
 
 
