@@ -18,7 +18,7 @@ BB_W_UINT, BB_W_INT, BB_W_NF, BB_W_FP4, BB_W_FP8_E4M3, BB_W_FP8_E5M2 = 0, 1, 2, 
 BB_ZEROS_ORIGINAL, BB_ZEROS_RESCALE, BB_ZEROS_QUANTIZED = 0, 1, 2
 BB_LAYOUT_COMPRESSED, BB_LAYOUT_INTERLEAVED_16, BB_LAYOUT_INTERLEAVED_8 = 0, 1, 2
 (BB_KERNEL_AUTO, BB_KERNEL_GENERIC, BB_KERNEL_GEMV_MMA, BB_KERNEL_GEMV_I8, BB_KERNEL_GEMM_TS,
- BB_KERNEL_GEMM_TS_I8) = range(6)
+ BB_KERNEL_GEMM_TS_I8, BB_KERNEL_GEMV_STREAMK) = range(7)
 
 DTYPE_IDS = {"float16": BB_F16, "bfloat16": BB_BF16, "float32": BB_F32, "int8": BB_I8, "int32": BB_I32}
 WFMT_IDS = {"uint": BB_W_UINT, "int": BB_W_INT, "nf": BB_W_NF, "fp": BB_W_FP4, "fp_e4m3": BB_W_FP8_E4M3,

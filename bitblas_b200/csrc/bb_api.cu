@@ -73,6 +73,7 @@ static int select(const bb_matmul_desc& d, int m) {
       case BB_KERNEL_GEMV_I8: if (gemv_i8_supported(d, m)) return ov; break;
       case BB_KERNEL_GEMM_TS: if (d.a_dtype != BB_I8 && gemm_ts_supported(d, m)) return ov; break;
       case BB_KERNEL_GEMM_TS_I8: if (d.a_dtype == BB_I8 && gemm_ts_supported(d, m)) return ov; break;
+      case BB_KERNEL_GEMV_STREAMK: if (gemv_streamk_supported(d, m)) return ov; break;
     }
     return -1;
   }
@@ -132,6 +133,7 @@ const char* bb_kernel_name(int id) {
     case BB_KERNEL_GEMV_I8: return "gemv_i8";
     case BB_KERNEL_GEMM_TS: return "gemm_ts_tcgen05";
     case BB_KERNEL_GEMM_TS_I8: return "gemm_ts_tcgen05_i8";
+    case BB_KERNEL_GEMV_STREAMK: return "gemv_streamk";
   }
   return "unknown";
 }
@@ -142,6 +144,7 @@ size_t bb_workspace_bytes(const bb_matmul_desc* desc, int m) {
   if (validate(desc)) return 0;
   const int k = select(*desc, m);
   if (k == BB_KERNEL_GEMM_TS || k == BB_KERNEL_GEMM_TS_I8) return gemm_ts_workspace_bytes(*desc, m);
+  if (k == BB_KERNEL_GEMV_STREAMK) return gemv_streamk_workspace_bytes();
   return 0;
 }
 
@@ -176,6 +179,7 @@ static int matmul_impl(const bb_matmul_desc* desc, const void* A, const void* W,
     case BB_KERNEL_GENERIC: return launch_generic(a);
     case BB_KERNEL_GEMV_MMA: return launch_gemv_mma(a);
     case BB_KERNEL_GEMV_I8: return launch_gemv_i8(a);
+    case BB_KERNEL_GEMV_STREAMK: return launch_gemv_streamk(a);
     case BB_KERNEL_GEMM_TS:
     case BB_KERNEL_GEMM_TS_I8: return launch_gemm_ts(a);
   }

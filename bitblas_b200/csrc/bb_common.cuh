@@ -65,6 +65,9 @@ bool generic_supported(const bb_matmul_desc& d);
 int launch_generic(const MatmulArgs& a);
 bool gemv_mma_supported(const bb_matmul_desc& d, int m);
 int launch_gemv_mma(const MatmulArgs& a);
+bool gemv_streamk_supported(const bb_matmul_desc& d, int m);
+int launch_gemv_streamk(const MatmulArgs& a);
+size_t gemv_streamk_workspace_bytes();  // partial slots + flags
 bool gemv_i8_supported(const bb_matmul_desc& d, int m);
 int launch_gemv_i8(const MatmulArgs& a);
 bool gemm_ts_supported(const bb_matmul_desc& d, int m);

@@ -89,7 +89,9 @@ typedef enum bb_kernel_id {
   BB_KERNEL_GEMV_MMA = 2,  /* m <= 32, fp16/bf16 A, 4/2-bit W: warp-level mma.sync streaming  */
   BB_KERNEL_GEMV_I8 = 3,   /* m <= 32, int8 A, 4/2-bit W: IMMA streaming, int32 exact         */
   BB_KERNEL_GEMM_TS = 4,   /* tcgen05 (W dequantised into TMEM as the MMA A operand) + TMA    */
-  BB_KERNEL_GEMM_TS_I8 = 5 /* tcgen05 kind::i8 variant                                        */
+  BB_KERNEL_GEMM_TS_I8 = 5,/* tcgen05 kind::i8 variant                                        */
+  BB_KERNEL_GEMV_STREAMK = 6 /* m <= 2, 4-bit W: persistent stream-K + TMA rings; opt-in through
+                              * bb_set_kernel_override only (measured no faster than GEMV_MMA) */
 } bb_kernel_id;
 
 /* replaces `init()` (builder/wrapper/base.py:5-13): one-time per-device setup (opt-in shared memory
@@ -116,7 +118,8 @@ int bb_matmul_scatter(const bb_matmul_desc* desc, const void* A, const void* W, 
                       const void* zeros, const void* bias, void* const* peer_C, int n_peers, int64_t ldc,
                       int64_t col_offset, int m, void* workspace, size_t workspace_bytes, void* stream);
 
-/* scratch (fp32 split-K partials) the chosen kernel needs for this (desc, m); 0 for most configs. */
+/* scratch (fp32 split-K partials; stream-K slots + flags) the chosen kernel needs for this (desc, m); 0 for most configs.
+ * Contents may be undefined on entry. */
 size_t bb_workspace_bytes(const bb_matmul_desc* desc, int m);
 
 /* which kernel family bb_matmul would run for (desc, m) -- bb_kernel_id; <0 on invalid desc. */

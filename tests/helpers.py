@@ -86,12 +86,14 @@ def run_product(op, case, device="cuda"):
     return out.cpu()
 
 
-def assert_fp_close(got, ref, what=""):
+def assert_fp_close(got, ref, what="", max_mismatched_ratio=0.0):
     """north_star tolerance: <= 1e-2 relative for FP accumulate.  Checked two ways: normwise relative error
     <= 1e-2 and the reference's own elementwise criterion (rtol=1e-2, atol=1e-2, torch_assert_close) with NO
-    mismatches allowed (the reference allows 5 %)."""
+    mismatches allowed by default (the reference allows 5 %; bfloat16-output cases with thousands of outputs pass
+    max_mismatched_ratio=2e-3: one bf16 ulp is up to 0.78 % of the value, so a double-rounding difference of two ulps
+    between the fp32-accumulating kernel and the oracle's A_dtype-accumulate emulation can exceed rtol on single elements)."""
     err = O.rel_fro_error(got, ref)
     assert err <= 1e-2, f"{what}: normwise rel err {err:.3e} > 1e-2"
     O.torch_assert_close(got.float(), ref.float(), rtol=1e-2, atol=1e-2 * max(1.0, float(ref.float().abs().mean())),
-                         max_mismatched_ratio=0.0)
+                         max_mismatched_ratio=max_mismatched_ratio)
     return err
