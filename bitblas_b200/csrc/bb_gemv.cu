@@ -79,6 +79,18 @@ __device__ __forceinline__ float raw_to_float(uint16_t b) {
   return TypeTraits<T>::to_float(*reinterpret_cast<const T*>(&b));
 }
 
+// Programmatic dependent launch (PDL).  A decode step is a chain of dependent GEMVs (qkv -> o -> gate_up -> down); the
+// weights, scales and zeros of the next one do not depend on the previous result, only its activations do.  Each streaming
+// kernel therefore (1) lets the next kernel in the stream start once every CTA of its own has finished its weight stream
+// (pdl_launch_dependents before the epilogue; triggering at kernel entry was measured: the early CTAs of kernel i+1 then
+// compete with kernel i and the big shapes got 15-20 % slower) and (2) starts its own weight prefetch immediately but
+// executes pdl_wait -- which
+// returns once the preceding kernel has completed and flushed -- before the first activation load.  Launch latency and the
+// first DRAM round trip of kernel i+1 then overlap the tail of kernel i.  Both instructions are no-ops when the launch
+// carries no programmatic-serialization attribute or the predecessor never triggers.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int BITS>
 __device__ __forceinline__ void load_w(const uint8_t* p, uint32_t (&w)[BITS]) {
   if constexpr (BITS == 4) {
@@ -432,6 +444,7 @@ gemv_mma_kernel(const GemvParams p) {
       wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
     }
     fetch_group();   // first group's parameters: the only synchronous fetch, overlapped with the weight prologue
+    pdl_wait();      // weights / scales / zeros above are not produced by the preceding kernel; the activations below may be
     begin_group();
     // GUARD = false: the chunk and all of its refills are inside the range (no per-step predicates)
     auto chunk = [&](auto guard_tag, int s, int buf) {
@@ -455,6 +468,8 @@ gemv_mma_kernel(const GemvParams p) {
   }
 
   // cross-warp reduction + epilogue
+  if (ns <= 0) pdl_wait();   // (every path waits before it stores: the preceding kernel may still read what we overwrite)
+  pdl_launch_dependents();   // the weight stream of this CTA is done: let the next kernel's CTAs take the freed slots
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
     red[warp][r][8 * t + 2 * q] = acc_t[t][0];
@@ -529,6 +544,7 @@ struct SkParams {
   int CPR;                       // chunks per row block = K / 256
   int WPR;                       // parameter windows per row = G / 8
   int lg_spg;                    // log2(steps per group); group sizes are 128 << lg_spg
+  int depth;                     // ring slots in use per warp (1 .. SK_DEPTH)
   long long T;                   // chunks in total
   int Wtot;                      // consumer warps in the grid
   float* slots;                  // [Wtot][SK_SLOT_FLOATS]
@@ -618,6 +634,7 @@ gemv_sk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int c = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   // every warp is its own producer: barriers, ring and window slots are private to the warp
   const uint32_t abytes = 512u * uint32_t(p.M);
+  const int DEPTH = sp.depth;   // ring slots in use (<= SK_DEPTH, the allocation)
   const uint32_t smem0 = (sk_smem_u32(sk_raw) + 1023u) & ~1023u;
   const uint32_t wring_c = smem0 + uint32_t(c * SK_DEPTH) * SK_WBYTES;
   const uint32_t aring_c = smem0 + SK_CONSUMERS * SK_DEPTH * SK_WBYTES + uint32_t(c * SK_DEPTH) * abytes;
@@ -656,7 +673,7 @@ gemv_sk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       sk_tma_2d(wring_c + uint32_t(islot) * SK_WBYTES, &tmW, ic0, irb16, bar);
       sk_tma_2d(aring_c + uint32_t(islot) * abytes, &tmA, 2 * ic0, 0, bar);
     }
-    if (++islot == SK_DEPTH) islot = 0;
+    if (++islot == DEPTH) islot = 0;
     ++ti;
     ic0 += 128;
     if (ic0 == Kb) { ic0 = 0; irb16 += 16; }
@@ -678,7 +695,7 @@ gemv_sk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   issue_window();
   if (wmore) issue_window();
 #pragma unroll 1
-  for (int i = 0; i < SK_DEPTH && ti < t1; ++i) issue_chunk();
+  for (int i = 0; i < DEPTH && ti < t1; ++i) issue_chunk();
 
   // ---- consume side ----
   int cslot = 0, nwin = 0;
@@ -754,7 +771,7 @@ gemv_sk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       sk_mbar_wait(barF + uint32_t(cslot) * 8u, cphase);
       const uint32_t tile = wring_c + uint32_t(cslot) * SK_WBYTES;
       const uint32_t atile = aring_c + uint32_t(cslot) * abytes + a_off;
-      if (++cslot == SK_DEPTH) { cslot = 0; cphase ^= 1u; }
+      if (++cslot == DEPTH) { cslot = 0; cphase ^= 1u; }
       uint32_t wreg[2][2][4], R[2][16];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -951,6 +968,7 @@ gemv_i8_kernel(const GemvParams p) {
       if (u < ns) { load_w<BITS>(wnext_a, wq[u][0]); load_w<BITS>(wnext_b, wq[u][1]); }
       wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
     }
+    pdl_wait();
     auto chunk = [&](auto guard_tag, int s) {
       constexpr bool GUARD = decltype(guard_tag)::value;
 #pragma unroll
@@ -968,6 +986,8 @@ gemv_i8_kernel(const GemvParams p) {
 #pragma unroll 1
     for (; s < ns; s += PF) chunk(std::true_type{}, s);
   }
+  if (ns <= 0) pdl_wait();
+  pdl_launch_dependents();
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
 #pragma unroll
@@ -1031,6 +1051,11 @@ int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_bl
   return 1;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("BB_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
 #define BB_GEMV_GO(KERNEL, MAXKS)                                              \
   {                                                                            \
     static int occ_cache_store[5][MAX_KS + 1];                                 \
@@ -1039,7 +1064,14 @@ int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_bl
     if (stage_bytes) for (int& v : occ_cache_store[1]) v = -1;  /* staged: smem depends on K -> recompute */ \
     int (&occ_cache)[MAX_KS + 1] = occ_cache_store[stage_bytes ? 1 : 0];       \
     p.ks = pick_ks(KERNEL, occ_cache, MAXKS, nb, p.K / 128, stage_bytes);      \
-    KERNEL<<<nb, p.ks * 32, stage_bytes, a.stream>>>(p);                       \
+    cudaLaunchConfig_t cfg = {};                                               \
+    cfg.gridDim = dim3(nb); cfg.blockDim = dim3(p.ks * 32);                    \
+    cfg.dynamicSmemBytes = stage_bytes; cfg.stream = a.stream;                 \
+    cudaLaunchAttribute attr[1];                                               \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;           \
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0; \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                        \
+    BB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, KERNEL, p));                        \
   }
 
 typedef CUresult (*SkEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1117,6 +1149,8 @@ int launch_gemv_sk(const MatmulArgs& a, const GemvParams& p) {
   sp.WPR = p.G / SK_WIN_GROUPS;
   sp.lg_spg = 0;
   while ((128 << sp.lg_spg) < p.g) ++sp.lg_spg;
+  static const int depth_env = [] { const char* e = getenv("BB_SK_DEPTH"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= SK_DEPTH) ? v : SK_DEPTH; }();
+  sp.depth = depth_env;
   sp.T = (long long)(p.N / 16) * sp.CPR;
   const int smem = sk_smem_bytes(p.M);
   int grid = 0;

@@ -146,6 +146,40 @@ def test_gemv_streamk_graph_replay_and_errors():
         lib.bb_set_kernel_override(prev)
 
 
+def test_gemv_pdl_dependent_chain():
+    """Programmatic dependent launch: kernel i+1 starts (and prefetches weights) before kernel i has finished, and must
+    still see kernel i's output as its activations and never overwrite a buffer kernel i is still reading.  A chain
+    y = W2 (W1 x) is launched 24 times back to back without any synchronisation, re-using the intermediate buffer, then
+    every result is compared bit-for-bit with the same chain run with a device synchronisation after every launch."""
+    torch.manual_seed(3)
+    dev = "cuda"
+    c1 = H.make_case(1, 2048, 1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized", seed=1)
+    c2 = H.make_case(1, 512, 2048, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized", seed=2)
+    op1, op2 = H.product_operator(c1), H.product_operator(c2)
+    assert op1.kernel_for(1) == "gemv_mma" and op2.kernel_for(1) == "gemv_mma"
+    W1, W2 = H.product_weight(op1, c1, dev), H.product_weight(op2, c2, dev)
+    s1, z1, s2, z2 = c1["scale"].to(dev), c1["zeros"].to(dev), c2["scale"].to(dev), c2["zeros"].to(dev)
+    xs = [((torch.rand(1, 1024) - 0.5) * 0.5).half().to(dev) for _ in range(24)]
+    mid = torch.empty(1, 2048, dtype=torch.float16, device=dev)
+    outs = [torch.empty(1, 512, dtype=torch.float16, device=dev) for _ in xs]
+    torch.cuda.synchronize()
+    for x, o in zip(xs, outs):          # no synchronisation anywhere in this loop
+        op1.forward(x, W1, scale=s1, zeros=z1, output=mid)
+        op2.forward(mid, W2, scale=s2, zeros=z2, output=o)
+    torch.cuda.synchronize()
+    got = [o.cpu() for o in outs]
+    for x, g in zip(xs, got):
+        op1.forward(x, W1, scale=s1, zeros=z1, output=mid)
+        torch.cuda.synchronize()
+        ref = op2.forward(mid, W2, scale=s2, zeros=z2)
+        torch.cuda.synchronize()
+        assert torch.equal(g, ref.cpu())
+    # and the chain is numerically the oracle's
+    mid_ref = H.oracle_output(dict(c1, A=xs[-1].cpu()), fast_decoding=bool(op1.fast_decoding))
+    out_ref = H.oracle_output(dict(c2, A=mid_ref.to(torch.float16)), fast_decoding=bool(op2.fast_decoding))
+    H.assert_fp_close(got[-1], out_ref, "pdl chain")
+
+
 GEMM_CASES = [
     # reference GEMM cases (test_general_matmul_ops_backend_tl.py:337-343), M=256 N=K=256
     dict(M=256, N=256, K=256, W_dtype="uint4"),

@@ -8,6 +8,9 @@ shapes = [(12288, 12288), (9472, 12288), (14208, 12288), (8192, 8192), (28672, 8
 if os.environ.get("AB_SHAPES"):
     shapes = [tuple(int(v) for v in t.split("x")) for t in os.environ["AB_SHAPES"].split(",")]
 reps_env = int(os.environ.get("AB_REPS", "60"))
+from bitblas_b200 import _lib
+if os.environ.get("AB_KERNEL"):
+    _lib.load().bb_set_kernel_override(int(os.environ["AB_KERNEL"]))
 ms = [int(x) for x in os.environ.get("AB_M", "1").split(",")]
 for (N, K) in shapes:
     for m in ms:
@@ -29,5 +32,5 @@ for (N, K) in shapes:
         e.record(); torch.cuda.synchronize()
         us = s.elapsed_time(e) / reps * 1000
         byt = N * K / 2 + N * (K // 128) * 2.5 + m * K * 2 + m * N * 2
-        print(f"N={N} K={K} m={m} {us:.1f} us  {byt / us / 1e3:.0f} GB/s  TMA={os.environ.get('BB_GEMV_TMA','1')} MINB={os.environ.get('BB_GEMV_TMA_MINB','auto')}", flush=True)
+        print(f"N={N} K={K} m={m} {us:.1f} us  {byt / us / 1e3:.0f} GB/s  kernel={op.kernel_for(m)} depth={os.environ.get('BB_SK_DEPTH','-')}", flush=True)
         del Ws
