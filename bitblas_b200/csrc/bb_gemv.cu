@@ -535,8 +535,8 @@ constexpr int SK_SLOT_FLOATS = 128;         // per-warp partial slot: 32 lanes x
 constexpr int SK_NBARS = SK_CONSUMERS * (SK_DEPTH + SK_WIN_SLOTS);
 constexpr int SK_MIN_CHUNKS = 4;            // do not spread a small problem thinner than this per warp
 
-__host__ __device__ constexpr int sk_smem_bytes(int M) {
-  return 1024 + SK_CONSUMERS * (SK_DEPTH * (SK_WBYTES + 512 * M) + SK_WIN_SLOTS * SK_WIN_BYTES) + SK_NBARS * 8;
+__host__ __device__ constexpr int sk_smem_bytes(int M, int depth) {
+  return 1024 + SK_CONSUMERS * (depth * (SK_WBYTES + 512 * M) + SK_WIN_SLOTS * SK_WIN_BYTES) + SK_NBARS * 8;
 }
 
 struct SkParams {
@@ -616,8 +616,10 @@ __device__ __forceinline__ void mma_16816_z<__nv_bfloat16>(float (&c)[4], const 
 }
 
 // GPC: quantisation groups per chunk -- 2 for group size 128 (one per MMA step), 1 for 256 << n
-template <typename T, bool IL, int ZK, int GPC>
-__global__ void __launch_bounds__(SK_THREADS, 2)
+// MINB: CTAs per SM the kernel is compiled for.  2: both MMA steps of a chunk staged in registers, four interleaved HMMA chains
+// (<= 128 registers); 3 / 4: one step at a time, two chains, <= 85 / 64 registers -- 24 / 32 warps per SM with a shallower ring.
+template <typename T, bool IL, int ZK, int GPC, int MINB>
+__global__ void __launch_bounds__(SK_THREADS, MINB)
 gemv_sk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmZ, const SkParams sp) {
   constexpr int NP = 4, WPS = 4;
@@ -634,12 +636,12 @@ gemv_sk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int c = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   // every warp is its own producer: barriers, ring and window slots are private to the warp
   const uint32_t abytes = 512u * uint32_t(p.M);
-  const int DEPTH = sp.depth;   // ring slots in use (<= SK_DEPTH, the allocation)
+  const int DEPTH = sp.depth;   // ring slots per warp (1 .. SK_DEPTH); the shared-memory layout follows it
   const uint32_t smem0 = (sk_smem_u32(sk_raw) + 1023u) & ~1023u;
-  const uint32_t wring_c = smem0 + uint32_t(c * SK_DEPTH) * SK_WBYTES;
-  const uint32_t aring_c = smem0 + SK_CONSUMERS * SK_DEPTH * SK_WBYTES + uint32_t(c * SK_DEPTH) * abytes;
-  const uint32_t wins_c = smem0 + SK_CONSUMERS * SK_DEPTH * (SK_WBYTES + abytes) + uint32_t(c * SK_WIN_SLOTS) * SK_WIN_BYTES;
-  const uint32_t bars = smem0 + SK_CONSUMERS * (SK_DEPTH * (SK_WBYTES + abytes) + SK_WIN_SLOTS * SK_WIN_BYTES);
+  const uint32_t wring_c = smem0 + uint32_t(c * DEPTH) * SK_WBYTES;
+  const uint32_t aring_c = smem0 + uint32_t(SK_CONSUMERS * DEPTH) * SK_WBYTES + uint32_t(c * DEPTH) * abytes;
+  const uint32_t wins_c = smem0 + uint32_t(SK_CONSUMERS * DEPTH) * (SK_WBYTES + abytes) + uint32_t(c * SK_WIN_SLOTS) * SK_WIN_BYTES;
+  const uint32_t bars = smem0 + uint32_t(SK_CONSUMERS) * (uint32_t(DEPTH) * (SK_WBYTES + abytes) + SK_WIN_SLOTS * SK_WIN_BYTES);
   const uint32_t barF = bars + uint32_t(c * (SK_DEPTH + SK_WIN_SLOTS)) * 8u;   // full[DEPTH] then pfull[2]
   const uint32_t barP = barF + SK_DEPTH * 8u;
   const int lg_spg = sp.lg_spg;   // steps per group = 1 << lg_spg
@@ -772,89 +774,153 @@ gemv_sk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       const uint32_t tile = wring_c + uint32_t(cslot) * SK_WBYTES;
       const uint32_t atile = aring_c + uint32_t(cslot) * abytes + a_off;
       if (++cslot == DEPTH) { cslot = 0; cphase ^= 1u; }
-      uint32_t wreg[2][2][4], R[2][16];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t ch16 = ((uint32_t(j * 4 + q)) ^ sw) * 16;
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wreg[j][0][0]), "=r"(wreg[j][0][1]), "=r"(wreg[j][0][2]), "=r"(wreg[j][0][3]) : "r"(tile + rowoff_a + ch16));
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wreg[j][1][0]), "=r"(wreg[j][1][1]), "=r"(wreg[j][1][2]), "=r"(wreg[j][1][3]) : "r"(tile + rowoff_b + ch16));
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(R[j][4 * x]), "=r"(R[j][4 * x + 1]), "=r"(R[j][4 * x + 2]), "=r"(R[j][4 * x + 3])
-                       : "r"(atile + uint32_t(j * 256 + x * 16)));
-      }
-      // The whole chunk is in registers: request the chunk DEPTH ahead into this slot while we compute.  No proxy fence:
-      // the ld.shared above were issued (in order, by every lane -- __syncwarp) before the request, complete within tens
-      // of cycles, and the TMA write lands after an L2 / DRAM round trip; a fence.proxy.async here (MEMBAR.ALL.CTA +
-      // FENCE.VIEW.ASYNC) measured ~10 % of all issue-stall samples.
-      if (ti < t1) {
-        __syncwarp();
-        issue_chunk();
-      }
-      // Group parameters of the two steps (GPC == 1: one group, both steps share it).
-      float s_a[2], s_b[2];
-      uint32_t fold2[2][4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (GPC == 2 || j == 0) {
-          if constexpr (ZK == 3) {
-            const uint2 z = (GPC == 2 && j == 1) ? z1 : z0;
-            set_fold((z.x >> zsh) & 15u, (z.y >> zsh) & 15u);
-          }
-          s_a[j] = raw_to_float<T>(uint16_t((GPC == 2 && j == 1) ? (sa2 >> 16) : sa2));
-          s_b[j] = raw_to_float<T>(uint16_t((GPC == 2 && j == 1) ? (sb2 >> 16) : sb2));
-        } else {
-          s_a[j] = s_a[0]; s_b[j] = s_b[0];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) fold2[j][u] = fold[u];
-      }
-      // The two MMA steps of the chunk are independent (separate accumulators), so their chains are interleaved: four
-      // dependent HMMA chains per warp instead of two -- the kernel is latency-bound at 4 warps per scheduler.
-      float acc_w[2][4], acc_f[2][4];
-#pragma unroll
-      for (int wi = 0; wi < WPS; ++wi) {
-        uint32_t ha[2][NP], hb[2][NP];
+      if constexpr (MINB == 2) {
+        uint32_t wreg[2][2][4], R[2][16];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          if constexpr (HI) {
-            const uint32_t xa = wreg[j][0][wi], ya = wreg[j][0][wi] >> 8, xb = wreg[j][1][wi], yb = wreg[j][1][wi] >> 8;
-            ha[j][0] = lop3_and_or(xa, 0x000f000fu, MAGIC); ha[j][1] = lop3_and_or(xa, 0x00f000f0u, MAGIC_HI);
-            ha[j][2] = lop3_and_or(ya, 0x000f000fu, MAGIC); ha[j][3] = lop3_and_or(ya, 0x00f000f0u, MAGIC_HI);
-            hb[j][0] = lop3_and_or(xb, 0x000f000fu, MAGIC); hb[j][1] = lop3_and_or(xb, 0x00f000f0u, MAGIC_HI);
-            hb[j][2] = lop3_and_or(yb, 0x000f000fu, MAGIC); hb[j][3] = lop3_and_or(yb, 0x00f000f0u, MAGIC_HI);
-          } else {
-            decode_u4x8_raw<T>(wreg[j][0][wi], ha[j]);
-            decode_u4x8_raw<T>(wreg[j][1][wi], hb[j]);
-          }
-        }
+          const uint32_t ch16 = ((uint32_t(j * 4 + q)) ^ sw) * 16;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wreg[j][0][0]), "=r"(wreg[j][0][1]), "=r"(wreg[j][0][2]), "=r"(wreg[j][0][3]) : "r"(tile + rowoff_a + ch16));
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wreg[j][1][0]), "=r"(wreg[j][1][1]), "=r"(wreg[j][1][2]), "=r"(wreg[j][1][3]) : "r"(tile + rowoff_b + ch16));
 #pragma unroll
-        for (int jj = 0; jj < NP / 2; ++jj) {
+          for (int x = 0; x < 4; ++x)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(R[j][4 * x]), "=r"(R[j][4 * x + 1]), "=r"(R[j][4 * x + 2]), "=r"(R[j][4 * x + 3])
+                         : "r"(atile + uint32_t(j * 256 + x * 16)));
+        }
+        // The whole chunk is in registers: request the chunk DEPTH ahead into this slot while we compute.  No proxy fence:
+        // the ld.shared above were issued (in order, by every lane -- __syncwarp) before the request, complete within tens
+        // of cycles, and the TMA write lands after an L2 / DRAM round trip; a fence.proxy.async here (MEMBAR.ALL.CTA +
+        // FENCE.VIEW.ASYNC) measured ~10 % of all issue-stall samples.
+        if (ti < t1) {
+          __syncwarp();
+          issue_chunk();
+        }
+        // Group parameters of the two steps (GPC == 1: one group, both steps share it).
+        float s_a[2], s_b[2];
+        uint32_t fold2[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (GPC == 2 || j == 0) {
+            if constexpr (ZK == 3) {
+              const uint2 z = (GPC == 2 && j == 1) ? z1 : z0;
+              set_fold((z.x >> zsh) & 15u, (z.y >> zsh) & 15u);
+            }
+            s_a[j] = raw_to_float<T>(uint16_t((GPC == 2 && j == 1) ? (sa2 >> 16) : sa2));
+            s_b[j] = raw_to_float<T>(uint16_t((GPC == 2 && j == 1) ? (sb2 >> 16) : sb2));
+          } else {
+            s_a[j] = s_a[0]; s_b[j] = s_b[0];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) fold2[j][u] = fold[u];
+        }
+        // The two MMA steps of the chunk are independent (separate accumulators), so their chains are interleaved: four
+        // dependent HMMA chains per warp instead of two -- the kernel is latency-bound at 4 warps per scheduler.
+        float acc_w[2][4], acc_f[2][4];
+#pragma unroll
+        for (int wi = 0; wi < WPS; ++wi) {
+          uint32_t ha[2][NP], hb[2][NP];
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const uint32_t af[4] = {ha[j][2 * jj], hb[j][2 * jj], ha[j][2 * jj + 1], hb[j][2 * jj + 1]};
-            uint32_t b0, b1;
-            if constexpr (IL) {
-              b0 = R[j][wi * NP + 2 * jj]; b1 = R[j][wi * NP + 2 * jj + 1];
+            if constexpr (HI) {
+              const uint32_t xa = wreg[j][0][wi], ya = wreg[j][0][wi] >> 8, xb = wreg[j][1][wi], yb = wreg[j][1][wi] >> 8;
+              ha[j][0] = lop3_and_or(xa, 0x000f000fu, MAGIC); ha[j][1] = lop3_and_or(xa, 0x00f000f0u, MAGIC_HI);
+              ha[j][2] = lop3_and_or(ya, 0x000f000fu, MAGIC); ha[j][3] = lop3_and_or(ya, 0x00f000f0u, MAGIC_HI);
+              hb[j][0] = lop3_and_or(xb, 0x000f000fu, MAGIC); hb[j][1] = lop3_and_or(xb, 0x00f000f0u, MAGIC_HI);
+              hb[j][2] = lop3_and_or(yb, 0x000f000fu, MAGIC); hb[j][3] = lop3_and_or(yb, 0x00f000f0u, MAGIC_HI);
             } else {
-              b0 = __byte_perm(R[j][wi * NP + jj], R[j][wi * NP + jj + NP / 2], 0x5410);
-              b1 = __byte_perm(R[j][wi * NP + jj], R[j][wi * NP + jj + NP / 2], 0x7632);
+              decode_u4x8_raw<T>(wreg[j][0][wi], ha[j]);
+              decode_u4x8_raw<T>(wreg[j][1][wi], hb[j]);
             }
-            if (wi == 0 && jj == 0) {   // first MMA of each chain: C = 0, accumulators never need zeroing
-              mma_16816_z<T>(acc_w[j], af, b0, b1);
-              mma_16816_z<T>(acc_f[j], fold2[j], b0, b1);
-            } else {
-              mma_16816<T>(acc_w[j], af, b0, b1);
-              mma_16816<T>(acc_f[j], fold2[j], b0, b1);
+          }
+#pragma unroll
+          for (int jj = 0; jj < NP / 2; ++jj) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t af[4] = {ha[j][2 * jj], hb[j][2 * jj], ha[j][2 * jj + 1], hb[j][2 * jj + 1]};
+              uint32_t b0, b1;
+              if constexpr (IL) {
+                b0 = R[j][wi * NP + 2 * jj]; b1 = R[j][wi * NP + 2 * jj + 1];
+              } else {
+                b0 = __byte_perm(R[j][wi * NP + jj], R[j][wi * NP + jj + NP / 2], 0x5410);
+                b1 = __byte_perm(R[j][wi * NP + jj], R[j][wi * NP + jj + NP / 2], 0x7632);
+              }
+              if (wi == 0 && jj == 0) {   // first MMA of each chain: C = 0, accumulators never need zeroing
+                mma_16816_z<T>(acc_w[j], af, b0, b1);
+                mma_16816_z<T>(acc_f[j], fold2[j], b0, b1);
+              } else {
+                mma_16816<T>(acc_w[j], af, b0, b1);
+                mma_16816<T>(acc_f[j], fold2[j], b0, b1);
+              }
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc_t[u] = fmaf((u < 2) ? s_a[j] : s_b[j], acc_w[j][u] + acc_f[j][u], acc_t[u]);
+          } else {
+        // ---- lean variant: one MMA step at a time (24 live data registers instead of 48), two chains ----
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t wa[4], wb[4], Rj[16];
+          const uint32_t ch16 = ((uint32_t(j * 4 + q)) ^ sw) * 16;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wa[0]), "=r"(wa[1]), "=r"(wa[2]), "=r"(wa[3]) : "r"(tile + rowoff_a + ch16));
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wb[0]), "=r"(wb[1]), "=r"(wb[2]), "=r"(wb[3]) : "r"(tile + rowoff_b + ch16));
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(Rj[4 * x]), "=r"(Rj[4 * x + 1]), "=r"(Rj[4 * x + 2]), "=r"(Rj[4 * x + 3])
+                         : "r"(atile + uint32_t(j * 256 + x * 16)));
+          if (j == 1 && ti < t1) {   // the second step has left the slot: request the chunk DEPTH ahead into it
+            __syncwarp();
+            issue_chunk();
+          }
+          float s_a, s_b;
+          if (GPC == 2 || j == 0) {
+            if constexpr (ZK == 3) {
+              const uint2 z = (GPC == 2 && j == 1) ? z1 : z0;
+              set_fold((z.x >> zsh) & 15u, (z.y >> zsh) & 15u);
+            }
+          }
+          s_a = raw_to_float<T>(uint16_t((GPC == 2 && j == 1) ? (sa2 >> 16) : sa2));
+          s_b = raw_to_float<T>(uint16_t((GPC == 2 && j == 1) ? (sb2 >> 16) : sb2));
+          float acc_w[4], acc_f[4];
+#pragma unroll
+          for (int wi = 0; wi < WPS; ++wi) {
+            uint32_t ha[NP], hb[NP];
+            if constexpr (HI) {
+              const uint32_t xa = wa[wi], ya = wa[wi] >> 8, xb = wb[wi], yb = wb[wi] >> 8;
+              ha[0] = lop3_and_or(xa, 0x000f000fu, MAGIC); ha[1] = lop3_and_or(xa, 0x00f000f0u, MAGIC_HI);
+              ha[2] = lop3_and_or(ya, 0x000f000fu, MAGIC); ha[3] = lop3_and_or(ya, 0x00f000f0u, MAGIC_HI);
+              hb[0] = lop3_and_or(xb, 0x000f000fu, MAGIC); hb[1] = lop3_and_or(xb, 0x00f000f0u, MAGIC_HI);
+              hb[2] = lop3_and_or(yb, 0x000f000fu, MAGIC); hb[3] = lop3_and_or(yb, 0x00f000f0u, MAGIC_HI);
+            } else {
+              decode_u4x8_raw<T>(wa[wi], ha);
+              decode_u4x8_raw<T>(wb[wi], hb);
+            }
+#pragma unroll
+            for (int jj = 0; jj < NP / 2; ++jj) {
+              const uint32_t af[4] = {ha[2 * jj], hb[2 * jj], ha[2 * jj + 1], hb[2 * jj + 1]};
+              uint32_t b0, b1;
+              if constexpr (IL) {
+                b0 = Rj[wi * NP + 2 * jj]; b1 = Rj[wi * NP + 2 * jj + 1];
+              } else {
+                b0 = __byte_perm(Rj[wi * NP + jj], Rj[wi * NP + jj + NP / 2], 0x5410);
+                b1 = __byte_perm(Rj[wi * NP + jj], Rj[wi * NP + jj + NP / 2], 0x7632);
+              }
+              if (wi == 0 && jj == 0) {
+                mma_16816_z<T>(acc_w, af, b0, b1);
+                mma_16816_z<T>(acc_f, fold, b0, b1);
+              } else {
+                mma_16816<T>(acc_w, af, b0, b1);
+                mma_16816<T>(acc_f, fold, b0, b1);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc_t[u] = fmaf((u < 2) ? s_a : s_b, acc_w[u] + acc_f[u], acc_t[u]);
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc_t[u] = fmaf((u < 2) ? s_a[j] : s_b[j], acc_w[j][u] + acc_f[j][u], acc_t[u]);
     }
     t += seg_n;
 
@@ -1091,7 +1157,8 @@ int sk_sm_count() {
   static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
   return sms;
 }
-size_t sk_workspace_bytes() { return size_t(2 * sk_sm_count() * SK_CONSUMERS) * (SK_SLOT_FLOATS * 4 + 8) + 256; }
+constexpr int SK_MAX_MINB = 4;   // CTAs per SM of the densest variant (sizes the workspace)
+size_t sk_workspace_bytes() { return size_t(SK_MAX_MINB * sk_sm_count() * SK_CONSUMERS) * (SK_SLOT_FLOATS * 4 + 8) + 256; }
 
 bool gemv_sk_shape_ok(const bb_matmul_desc& d, int m) {
   if (m < 1 || m > SK_MAX_M || d.w_bits != 4 || !d.with_scaling) return false;
@@ -1152,17 +1219,18 @@ int launch_gemv_sk(const MatmulArgs& a, const GemvParams& p) {
   static const int depth_env = [] { const char* e = getenv("BB_SK_DEPTH"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= SK_DEPTH) ? v : SK_DEPTH; }();
   sp.depth = depth_env;
   sp.T = (long long)(p.N / 16) * sp.CPR;
-  const int smem = sk_smem_bytes(p.M);
+  static const int minb_env = [] { const char* e = getenv("BB_SK_MINB"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= SK_MAX_MINB) ? v : 2; }();
+  const int smem = sk_smem_bytes(p.M, sp.depth);
   int grid = 0;
-#define BB_SK_GO(ZKV, GPCV)                                                                                            \
+#define BB_SK_GO2(ZKV, GPCV, MB)                                                                                            \
   {                                                                                                                \
-    auto k = gemv_sk_kernel<T, IL, ZKV, GPCV>;                                                                     \
+    auto k = gemv_sk_kernel<T, IL, ZKV, GPCV, MB>;                                                                 \
     static int occ[SK_MAX_M + 1] = {0};                                                                            \
     if (!occ[p.M]) {                                                                                               \
-      BB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(SK_MAX_M))); \
+      BB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(SK_MAX_M, SK_DEPTH))); \
       int o = 0;                                                                                                   \
       BB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, SK_THREADS, size_t(smem)));               \
-      occ[p.M] = o < 1 ? -1 : (o > 2 ? 2 : o);                                                                     \
+      occ[p.M] = o < 1 ? -1 : (o > MB ? MB : o);                                                                   \
     }                                                                                                              \
     if (occ[p.M] < 0) { set_error("gemv_sk: kernel does not fit on this device"); return 4; }                      \
     const long long want = (sp.T + SK_CONSUMERS * SK_MIN_CHUNKS - 1) / (SK_CONSUMERS * SK_MIN_CHUNKS);            \
@@ -1172,16 +1240,22 @@ int launch_gemv_sk(const MatmulArgs& a, const GemvParams& p) {
   }
   // workspace: flags then slots; sized for the largest grid (2 CTAs per SM)
   sp.flags = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(a.workspace) + 15) & ~uintptr_t(15));
-  sp.slots = reinterpret_cast<float*>(sp.flags + 2 * sk_sm_count() * SK_CONSUMERS);
+  sp.slots = reinterpret_cast<float*>(sp.flags + SK_MAX_MINB * sk_sm_count() * SK_CONSUMERS);
   static std::atomic<unsigned long long> counter{0x9e3779b97f4a7c15ull};
   unsigned long long z = counter.fetch_add(0x9e3779b97f4a7c15ull);   // splitmix64: never 0 in practice, distinct per call
   z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
   z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
   sp.nonce = (z ^ (z >> 31)) | 1ull;
   if (sp.T >= (1ll << 31)) { set_error("gemv_sk: problem too large"); return 4; }
+  // the denser variants are instantiated for the headline configuration only (fp16, interleaved, quantized zeros, g = 128)
+#define BB_SK_GO(ZKV, GPCV)                                                                                       \
+  if constexpr (std::is_same<T, __half>::value && IL && ZKV == 3 && GPCV == 2) {                                  \
+    if (minb_env == 4) BB_SK_GO2(ZKV, GPCV, 4) else if (minb_env == 3) BB_SK_GO2(ZKV, GPCV, 3) else BB_SK_GO2(ZKV, GPCV, 2) \
+  } else BB_SK_GO2(ZKV, GPCV, 2)
   if (p.zmode == 3) { if (sp.lg_spg == 0) BB_SK_GO(3, 2) else BB_SK_GO(3, 1) }
   else { if (sp.lg_spg == 0) BB_SK_GO(0, 2) else BB_SK_GO(0, 1) }
 #undef BB_SK_GO
+#undef BB_SK_GO2
   BB_LAUNCH_CHECK();
   return 0;
 }
