@@ -379,7 +379,7 @@ def main():
     tgt = per_shape[-1]
     roofline = {"bound": "hbm", "kernel": "gemv_mma_kernel<half,4,interleaved,NT=1> N=K=12288", "achieved": tgt["GBps"],
                 "peak": pk["hbm"], "unit": "GB/s", "frac": tgt["frac_hbm"],
-                "traffic": 81.86e6 if world == 1 else None,  # dram read+write per launch, profiles/r1_gemv_mma_ncu_full.txt
+                "traffic": 80.75e6 if world == 1 else None,  # dram read+write per launch (78.51 + 2.24 MB), profiles/r1_gemv_mma_ncu_full.txt
                 "algorithmic_bytes": gemv_bytes(12288 // world, 12288), "us": tgt["us"], "peak_source": pk["src"],
                 "timing": "CUDA events around back-to-back launches cycling through >= 300 MB of read-only parameter copies (cold L2), per-launch average, median of 5"}
     result["gemv_shapes"] = per_shape
@@ -399,7 +399,7 @@ def main():
         result["gemm"] = {"M": M, "N": N, "K": K, "ms": round(ms, 4), "TFLOPS": round(tf, 1), "kernel": op.kernel_for(M),
                           "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": pk["tf"], "unit": "TFLOP/s",
                                        "frac": round(tf / pk["tf"], 3), "frac_of_sustained": round(tf / pk["tf_sustained"], 3) if pk["tf_sustained"] else None,
-                                       "traffic": 1275.6e6 if world == 1 else None,  # profiles/r1_gemm_ts_ncu_full.txt
+                                       "traffic": 1274.2e6 if world == 1 else None,  # dram read+write (1173.4 + 100.8 MB), profiles/r1_gemm_ts_ncu_full.txt
                                        "algorithmic_flops": 2.0 * M * N * K, "peak_source": pk["src"],
                                        "note": "A (100 MB) + W (75 MB) exceed L2; 10 back-to-back launches"}}
         small = []

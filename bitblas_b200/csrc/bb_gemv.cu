@@ -1100,12 +1100,16 @@ GemvParams make_params(const MatmulArgs& a) {
   return p;
 }
 
-// K splits per 16-row block: the largest warp count per CTA such that EVERY CTA of the grid is resident at once
-// (occupancy queried from the runtime for this kernel instantiation, cached).
+// K splits per 16-row block (= warps per CTA): the largest count for which EVERY CTA of the grid is resident at once
+// (occupancy queried from the runtime for this kernel instantiation, cached).  When not even two warps per CTA fit in one wave
+// (N >= ~24k rows), the full split is used and the grid runs in several waves: measured 40.9 us vs 44.4 us for one resident
+// warp per row block on 28672 x 8192 (20 instead of 12 warps per SM; `BB_GEMV_KS` sweeps it).
 template <typename KernelT>
 int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_blocks, int steps, int stage_bytes) {
   const int sms = device_sm_count();
-  for (int ks = max_ks; ks >= 1; --ks) {
+  static const int ks_env = [] { const char* e = getenv("BB_GEMV_KS"); return e ? atoi(e) : 0; }();   // tuning hook
+  if (ks_env >= 1 && ks_env <= max_ks && ks_env <= steps) return ks_env;
+  for (int ks = max_ks; ks >= 2; --ks) {
     if (ks > steps) continue;
     if (occ_cache[ks] < 0) {
       int occ = 0;
@@ -1114,7 +1118,7 @@ int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_bl
     }
     if (row_blocks <= sms * occ_cache[ks]) return ks;
   }
-  return 1;
+  return std::max(1, std::min(max_ks, steps));
 }
 
 bool pdl_enabled() {
