@@ -615,47 +615,81 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// out[m, n] = cast(sum_s ws[s][m][n]) (+ bias), stored to every destination of the OutSpec
+// out[m, n] = cast(sum_s ws[s][m][n]) (+ bias), stored to every destination of the OutSpec.  One thread = 4 consecutive n
+// (N is a multiple of 128 here): 128-bit loads of the partials, 32-bit index arithmetic, one vector store per destination.
 template <bool INT8>
 __global__ void splitk_reduce_kernel(const TsParams p) {
-  const size_t total = size_t(p.M) * p.N;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int m = int(i / p.N), n = int(i % p.N);
-    const size_t o = size_t(m) * size_t(p.out.ld) + size_t(p.out.col0) + n;
-    float bias_f = 0.f;
+  const unsigned n4 = unsigned(p.N) >> 2;                 // quads per row
+  const unsigned total4 = unsigned(p.M) * n4;             // m * N / 4 < 2^31 (m <= 128 on this path)
+  const size_t split_stride4 = size_t(p.M) * n4;          // quads per split
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const unsigned m = i / n4, n = (i - m * n4) * 4u;
+    float bias_f[4] = {0.f, 0.f, 0.f, 0.f};
     if (p.bias) {
-      if (p.a_dtype == BB_F16) bias_f = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
-      else if (p.a_dtype == BB_BF16) bias_f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
-      else bias_f = float(reinterpret_cast<const int8_t*>(p.bias)[n]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p.a_dtype == BB_F16) bias_f[j] = __half2float(reinterpret_cast<const __half*>(p.bias)[n + j]);
+        else if (p.a_dtype == BB_BF16) bias_f[j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n + j]);
+        else bias_f[j] = float(reinterpret_cast<const int8_t*>(p.bias)[n + j]);
+      }
     }
+    const size_t o = size_t(m) * size_t(p.out.ld) + size_t(p.out.col0) + n;
     if constexpr (INT8) {
-      int acc = 0;
-      for (int sp = 0; sp < p.splits; ++sp) acc += reinterpret_cast<const int*>(p.ws)[size_t(sp) * total + i];
-      const int b = int(bias_f);
+      int acc[4] = {0, 0, 0, 0};
+      for (int sp = 0; sp < p.splits; ++sp) {
+        const int4 v = __ldcs(reinterpret_cast<const int4*>(p.ws) + size_t(sp) * split_stride4 + i);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      }
       for (int d = 0; d < p.out.n; ++d) {
         void* Cd = p.out.ptr[d];
-        switch (p.out_dtype) {
-          case BB_I32: reinterpret_cast<int*>(Cd)[o] = acc + b; break;
-          case BB_I8: reinterpret_cast<int8_t*>(Cd)[o] = int8_t(int8_t(acc) + b); break;
-          case BB_F32: reinterpret_cast<float*>(Cd)[o] = float(acc) + float(b); break;
-          case BB_F16: reinterpret_cast<__half*>(Cd)[o] = __hadd(__int2half_rn(acc), __int2half_rn(b)); break;
-          default: reinterpret_cast<__nv_bfloat16*>(Cd)[o] = __hadd(__int2bfloat16_rn(acc), __int2bfloat16_rn(b));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int b = int(bias_f[j]);
+          switch (p.out_dtype) {
+            case BB_I32: reinterpret_cast<int*>(Cd)[o + j] = acc[j] + b; break;
+            case BB_I8: reinterpret_cast<int8_t*>(Cd)[o + j] = int8_t(int8_t(acc[j]) + b); break;
+            case BB_F32: reinterpret_cast<float*>(Cd)[o + j] = float(acc[j]) + float(b); break;
+            case BB_F16: reinterpret_cast<__half*>(Cd)[o + j] = __hadd(__int2half_rn(acc[j]), __int2half_rn(b)); break;
+            default: reinterpret_cast<__nv_bfloat16*>(Cd)[o + j] = __hadd(__int2bfloat16_rn(acc[j]), __int2bfloat16_rn(b));
+          }
         }
       }
     } else {
-      float acc = 0.f;
-      for (int sp = 0; sp < p.splits; ++sp) acc += reinterpret_cast<const float*>(p.ws)[size_t(sp) * total + i];
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int sp = 0; sp < p.splits; ++sp) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(p.ws) + size_t(sp) * split_stride4 + i);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      }
       if (p.out_dtype == BB_F16) {
-        __half h = __float2half_rn(acc);
-        if (p.bias) h = __hadd(h, __float2half_rn(bias_f));
-        for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__half*>(p.out.ptr[d])[o] = h;
+        __half h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[j] = __float2half_rn(acc[j]);
+          if (p.bias) h[j] = __hadd(h[j], __float2half_rn(bias_f[j]));
+        }
+        for (int d = 0; d < p.out.n; ++d) {
+          __half* dst = reinterpret_cast<__half*>(p.out.ptr[d]) + o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = h[j];
+        }
       } else if (p.out_dtype == BB_BF16) {
-        __nv_bfloat16 h = __float2bfloat16_rn(acc);
-        if (p.bias) h = __hadd(h, __float2bfloat16_rn(bias_f));
-        for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__nv_bfloat16*>(p.out.ptr[d])[o] = h;
+        __nv_bfloat16 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[j] = __float2bfloat16_rn(acc[j]);
+          if (p.bias) h[j] = __hadd(h[j], __float2bfloat16_rn(bias_f[j]));
+        }
+        for (int d = 0; d < p.out.n; ++d) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out.ptr[d]) + o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = h[j];
+        }
       } else {
-        const float f = acc + (p.bias ? bias_f : 0.f);
-        for (int d = 0; d < p.out.n; ++d) reinterpret_cast<float*>(p.out.ptr[d])[o] = f;
+        for (int d = 0; d < p.out.n; ++d) {
+          float* dst = reinterpret_cast<float*>(p.out.ptr[d]) + o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = acc[j] + (p.bias ? bias_f[j] : 0.f);
+        }
       }
     }
   }
@@ -749,7 +783,7 @@ int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
   kernel<<<grid, TS_THREADS, smem_bytes, a.stream>>>(tmA, tmW, p);
   BB_LAUNCH_CHECK();
   if (p.splits > 1) {
-    const size_t total = size_t(a.m) * a.d.N;
+    const size_t total = size_t(a.m) * a.d.N / 4;   // one thread per 4 consecutive n
     const int rthreads = 256;
     const int rblocks = int(std::min<size_t>((total + rthreads - 1) / rthreads, size_t(device_sm_count()) * 8));
     if (EI::kInt8) splitk_reduce_kernel<true><<<rblocks, rthreads, 0, a.stream>>>(p);
