@@ -16,6 +16,12 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # a kernel that hangs must fail its test, not the whole run (pytest-timeout is part of the image; without it the
+        # marker is inert)
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(300))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
