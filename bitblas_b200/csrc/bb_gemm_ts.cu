@@ -31,11 +31,16 @@ namespace bb {
 namespace {
 
 constexpr int TS_ROWS = 128;    // weight rows per CTA = MMA M
-constexpr int DQ_GROUPS = 2;                // dequant warp groups; group g decodes k-blocks kb = g (mod DQ_GROUPS)
-constexpr int DQ_WARPS_PER_GROUP = 8;       // 4 TMEM lane quadrants x 2 column halves
-constexpr int DQ_WARPS = DQ_GROUPS * DQ_WARPS_PER_GROUP;
+// 16 dequant warps = 4 TMEM lane quadrants x 4.  Two organisations (dq_groups(BM)):
+//  * BM > 128 (one CTA per SM, 36 KB stages, 6 of them): 2 groups x (4 quadrants x 2 column halves); a thread decodes HALF a row
+//    of its group's k-blocks.  A k-block leaves the dequant stage quickly, so at most two smem stages are pinned by decoding.
+//  * BM <= 128 (small stages, 8 of them): 4 groups x 4 quadrants; a thread decodes its WHOLE row (both halves) per iteration,
+//    so the barrier / slot bookkeeping -- about as many instructions as one half's decode -- is paid once per 64 weights
+//    (m = 16: 47 -> 38 us; with the large tile this organisation pins 4 of 6 stages and starves the TMA ring: 1285 -> 866 TFLOPS).
+constexpr int DQ_WARPS = 16;
+__host__ __device__ constexpr int dq_groups(int BM) { return BM > 128 ? 2 : 4; }
 constexpr int TS_THREADS = (2 + DQ_WARPS) * 32;
-constexpr int TA_SLOTS = 4;     // TMEM operand slots (k-blocks the dequant warps may run ahead)
+constexpr int TA_SLOTS = 4;     // TMEM operand slots (2 per dequant group with 2 groups, 1 per group with 4)
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -186,7 +191,8 @@ struct ElemInfo<int8_t> {
 template <int BM>
 struct TsTmem {
   static constexpr int kAcol0 = BM < 32 ? 32 : BM;
-  static constexpr int kNeed = kAcol0 + TA_SLOTS * 32;
+  static constexpr int kSlots = TA_SLOTS;
+  static constexpr int kNeed = kAcol0 + kSlots * 32;
   static constexpr int kCols = kNeed <= 64 ? 64 : (kNeed <= 128 ? 128 : (kNeed <= 256 ? 256 : 512));
 };
 
@@ -198,7 +204,7 @@ struct TsSmem {
   static constexpr int kStageBytes = kActBytes + kWBytes;
   static constexpr int kStagesRaw = (220 * 1024) / kStageBytes;
   static constexpr int kStages = (kStagesRaw > 8 ? 8 : kStagesRaw) & ~1;  // even: stage parity is static per dequant group
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 512;   // full[8] + empty[8] + a_ready[8] + a_free[8] + acc_full + tmem slot word
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
 };
 
@@ -375,7 +381,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < TA_SLOTS; ++i) { mbar_init(&a_ready[i], DQ_WARPS_PER_GROUP); mbar_init(&a_free[i], 1); }
+    for (int i = 0; i < TA_SLOTS; ++i) { mbar_init(&a_ready[i], DQ_WARPS / dq_groups(BM)); mbar_init(&a_free[i], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -424,14 +430,17 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_commit(&empty[s]);
         tc_commit(&a_free[t]);
         if (++s == S) { s = 0; spar ^= 1; }
-        if (++t == TA_SLOTS) { t = 0; tpar ^= 1; }
+        if (++t == TsTmem<BM>::kSlots) { t = 0; tpar ^= 1; }
       }
       tc_commit(acc_full);
     }
   } else {
     // ===== dequant warps (then epilogue) =====
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may touch
-    const int half = ((warp - 2) >> 2) & 1;            // which half of the k-block's columns
+    constexpr int DQ_GROUPS = dq_groups(BM);
+    constexpr int DQ_WARPS_PER_GROUP = DQ_WARPS / DQ_GROUPS;
+    constexpr bool WHOLE_ROW = DQ_GROUPS == 4;          // this thread decodes both halves of its row
+    const int half = WHOLE_ROW ? 0 : ((warp - 2) >> 2) & 1;   // which half of the k-block's columns (2-group organisation)
     const int grp = (warp - 2) / DQ_WARPS_PER_GROUP;   // which k-blocks (kb % DQ_GROUPS == grp)
     const int row = quad * 32 + lane;       // weight row inside the tile == TMEM lane
     const int n = n0 + row;
@@ -442,7 +451,9 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr bool HI = IL && !INT8 && std::is_same<TF, __half>::value && BITS == 4;
     constexpr uint32_t MAGIC_HI = HI ? 0x54005400u : MAGIC;
     constexpr int ZSH = HI ? 16 : 1;  // odd-nibble values are 64 + u: the folded zero point sits 4 mantissa bits up
-    static_assert(TA_SLOTS == 2 * DQ_GROUPS, "slot ownership is static per group");
+    constexpr int NSLOT = TsTmem<BM>::kSlots;
+    constexpr int SPG = NSLOT / DQ_GROUPS;   // operand slots per dequant group (1 or 2)
+    static_assert(NSLOT <= TA_SLOTS && SPG * DQ_GROUPS == NSLOT && (SPG == 1 || SPG == 2), "slot ownership is static per group");
     const int kb_per_g = p.g / KB;
     const uint16_t* sc_row = reinterpret_cast<const uint16_t*>(p.scale) + size_t(n) * p.G;
     const uint16_t* z_row = reinterpret_cast<const uint16_t*>(p.zeros) + size_t(n) * p.G;
@@ -474,8 +485,9 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (MODE != 0) fetch_group(gi);
       int st = grp;                      // smem stage of kb (S % DQ_GROUPS == 0 keeps stage parity per group)
       uint32_t full_par = 0;
-      uint32_t it = 0;                   // iteration count of this warp: slot = grp + DQ_GROUPS * (it & 1)
+      uint32_t it = 0;                   // iteration count of this warp: slot = grp + DQ_GROUPS * (it mod SPG)
       int prev_slot = -1;
+      const bool early_publish = S < DQ_GROUPS + 2;
       for (int kb = grp; kb < num_kb; kb += DQ_GROUPS) {
         if constexpr (MODE != 0) {
           if (kb >= g_end) {
@@ -497,6 +509,16 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (gi + g_step < p.G) fetch_group(gi + g_step);
           }
         }
+        // The previous k-block's slot is normally published AFTER this block's first decode (its tcgen05.st hides behind
+        // it).  With a pipeline no deeper than the group stride that order deadlocks: TMA(kb) waits for MMA(kb - S), which
+        // waits for exactly the slot this warp would publish only after TMA(kb) has landed -- publish first then.
+        if (early_publish && prev_slot >= 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[prev_slot]);
+          prev_slot = -1;
+        }
         mbar_wait(&full[st], full_par);
         uint32_t regs[16];
         if constexpr (INT8) dequant_half_row_i8<BITS, IL>(src0 + st * SM::kWBytes, regs, uint32_t(p.zp_const) * 0x01010101u);
@@ -508,12 +530,17 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[prev_slot]);
         }
-        const int slot = grp + DQ_GROUPS * int(it & 1);
-        if (it >= 2) {
-          mbar_wait(&a_free[slot], ((it >> 1) - 1) & 1);
+        const int slot = grp + DQ_GROUPS * int(it & (SPG - 1));
+        if (it >= SPG) {   // the MMAs that read this slot's previous contents must be done
+          mbar_wait(&a_free[slot], ((it / SPG) - 1) & 1);
           tc_fence_after();
         }
         tmem_st_x16(tdst0 + slot * 32, regs);
+        if constexpr (WHOLE_ROW) {
+          if constexpr (INT8) dequant_half_row_i8<BITS, IL>(src0 + st * SM::kWBytes + PRB / 2, regs, uint32_t(p.zp_const) * 0x01010101u);
+          else dequant_half_row<TF, BITS, MODE, IL>(src0 + st * SM::kWBytes + PRB / 2, regs, c);
+          tmem_st_x16(tdst0 + slot * 32 + 16, regs);
+        }
         prev_slot = slot;
         ++it;
         st += DQ_GROUPS;
@@ -541,7 +568,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ----- epilogue: accumulator[lane = n, column = m] -> C[m, n] -----
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    constexpr int CPH = BM / (2 * DQ_GROUPS);    // accumulator columns per warp
+    constexpr int CPH = BM / 4;                  // accumulator columns per warp (4 warps share a lane quadrant)
     constexpr int CH = CPH < 16 ? CPH : 16;      // columns per tcgen05.ld
     static_assert(CPH % CH == 0 && (CH == 16 || CH == 8), "BM must be >= 32");
     float bias_f = 0.f;
@@ -550,7 +577,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       else if (p.a_dtype == BB_BF16) bias_f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
       else bias_f = float(reinterpret_cast<const int8_t*>(p.bias)[n]);
     }
-    const int cbase = (grp * 2 + half) * CPH;
+    const int cbase = (WHOLE_ROW ? grp : grp * 2 + half) * CPH;
     void* const C0 = p.out.ptr[0];
     const int ndst = p.out.n;
     const size_t ld = size_t(p.out.ld), col0 = size_t(p.out.col0);
@@ -764,7 +791,7 @@ int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
     // more CTAs than SMs: keep the pipeline shallow enough for two resident CTAs (their windows add up); with at most
     // one CTA per SM the full depth is needed to cover the TMA latency
     const int cap = ((110 * 1024 - SM::kBarBytes - 1024) / SM::kStageBytes) & ~1;
-    if (cap >= 2 && cap < stages) stages = cap;
+    if (cap >= dq_groups(BM) && cap < stages) stages = cap;   // (a dequant group's first stage index is its group id)
   }
   p.stages = stages;
   const size_t smem_bytes = size_t(stages) * SM::kStageBytes + SM::kBarBytes + 1024;

@@ -202,6 +202,9 @@ GEMM_CASES = [
     dict(M=9, N=256, K=1024, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
     dict(M=16, N=128, K=2048, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original", with_bias=True),
     dict(M=32, N=256, K=1024, W_dtype="uint2", group_size=128, with_scaling=True),
+    # more CTAs than SMs at BM = 128: two CTAs per SM, pipeline capped to 4 stages (= the dequant group stride: the TMEM slot of
+    # a k-block must then be published BEFORE waiting for the next TMA stage, or the ring deadlocks)
+    dict(M=100, N=19200, K=512, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
     # split-K (few output tiles, long K): fp32 partials in the workspace + reduce kernel
     dict(M=64, N=128, K=4096, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized", with_bias=True),
     dict(M=40, N=256, K=8192, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="original"),
