@@ -394,6 +394,7 @@ class Matmul(Operator):
     def _workspace_for(self, m: int, device):
         """scratch for split-K partials (bb_workspace_bytes); one cached buffer per operator and device, grown on demand.
         Stream-ordered reuse: the reduce kernel of call i reads it before the matmul of call i+1 (same stream) writes it."""
+        # (the size depends on the kernel the dispatcher would pick, which a test may have pinned: not cached across overrides)
         need = int(self.lib._c.bb_workspace_bytes(ctypes.byref(self._desc), int(m)))
         if need == 0:
             return 0, 0
