@@ -19,6 +19,7 @@ oracle/bitblas_oracle.py -- on the host cores, on a bounded sample of the same w
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -276,6 +277,7 @@ def main():
     # NVLink), then one device-side barrier -- no separate collective (bb_matmul_scatter)
     fused = {"on": False}
     symm_cache = {}
+    peer_arrays = {}   # id(symmetric-memory handle) -> prebuilt (c_void_p * world) array of the peers' buffer pointers
     if world > 1 and os.environ.get("BB_BENCH_FUSED", "1") != "0":
         try:
             import torch.distributed._symmetric_memory as symm_mem
@@ -286,7 +288,10 @@ def main():
                     pairs = []
                     for _ in range(2):
                         t = symm_mem.empty((m, N), dtype=dtype, device=dev)
-                        pairs.append((t, symm_mem.rendezvous(t, dist.group.WORLD)))
+                        h = symm_mem.rendezvous(t, dist.group.WORLD)
+                        ptrs = [int(p) for p in h.buffer_ptrs]
+                        peer_arrays[id(h)] = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])  # built once
+                        pairs.append((t, h))
                     symm_cache[key] = [pairs, 0]
                 e = symm_cache[key]
                 t, h = e[0][e[1]]
@@ -311,7 +316,8 @@ def main():
         if fused["on"]:
             buf, hdl = symm_out(m, N_full, out_local.dtype, tag=id(op))
             op.forward_scatter(A, prm["W"], scale=prm["scale"], zeros=prm["zeros"],
-                               peer_ptrs=[int(p) for p in hdl.buffer_ptrs], ldc=N_full, col_offset=rank * (N_full // world))
+                               peer_ptrs=peer_arrays.get(id(hdl)) or [int(p) for p in hdl.buffer_ptrs],
+                               ldc=N_full, col_offset=rank * (N_full // world))
             if defer is not None:
                 defer.append(hdl)
             else:

@@ -417,7 +417,10 @@ class Matmul(Operator):
             raise ValueError(f"A has inner dimension {A.shape[-1]}, expected K={c.K}")
         m = reduce(_operator.mul, A.shape[:-1], 1)
         n = len(peer_ptrs)
-        arr = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(x)) for x in peer_ptrs])
+        if isinstance(peer_ptrs, ctypes.Array):   # prebuilt (c_void_p * n) array: callers on a hot path build it once per buffer
+            arr = peer_ptrs
+        else:
+            arr = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(x)) for x in peer_ptrs])
         dev = A.device.index if A.device.index is not None else torch.cuda.current_device()
         _lib.ensure_init(dev)
         stream = torch.cuda.current_stream(device=A.device).cuda_stream

@@ -14,6 +14,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import ctypes
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -104,22 +106,24 @@ class ColumnParallelLinear(nn.Module):
             for _ in range(2):  # double buffered: one barrier per call is enough (see forward)
                 t = symm_mem.empty((cap, self.out_features), dtype=dtype, device=device)
                 h = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
-                pairs.append((t, h))
+                ptrs = [int(p) for p in h.buffer_ptrs]
+                arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])   # built once per buffer
+                pairs.append((t, h, arr))
             self._symm[key] = [pairs, 0]
         entry = self._symm[key]
-        t, h = entry[0][entry[1]]
+        t, h, arr = entry[0][entry[1]]
         entry[1] ^= 1
-        return t, h
+        return t, h, arr
 
     def _forward_fused(self, x2: torch.Tensor) -> torch.Tensor:
         m = x2.shape[0]
         op = self.local.bitblas_matmul
         out_dtype = getattr(torch, op.out_dtype)
-        buf, hdl = self._symm_buffers(m, out_dtype, x2.device)
+        buf, hdl, peer_arr = self._symm_buffers(m, out_dtype, x2.device)
         lin = self.local
         op.forward_scatter(x2.contiguous(), lin.qweight, scale=lin.scales if op.with_scaling else None,
                            zeros=lin.zeros if op.with_zeros else None, bias=lin.bias if op.with_bias else None,
-                           peer_ptrs=[int(p) for p in hdl.buffer_ptrs], ldc=self.out_features, col_offset=self.n_lo)
+                           peer_ptrs=peer_arr, ldc=self.out_features, col_offset=self.n_lo)
         # every rank's slice has landed in every buffer once all ranks passed this point.  Buffers alternate between calls:
         # a rank can only overwrite buffer b again after the NEXT call's barrier, which every peer reaches after its
         # (stream-ordered) reads of this call's result.
