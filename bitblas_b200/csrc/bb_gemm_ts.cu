@@ -70,7 +70,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -179,13 +178,11 @@ template <typename T>
 struct ElemInfo {
   static constexpr bool kInt8 = false;
   static constexpr int kKB = 64;  // elements per 128-byte swizzle row
-  static constexpr int kUmmaK = 16;
 };
 template <>
 struct ElemInfo<int8_t> {
   static constexpr bool kInt8 = true;
   static constexpr int kKB = 128;
-  static constexpr int kUmmaK = 32;
 };
 
 template <int BM>

@@ -102,41 +102,6 @@ __device__ __forceinline__ void load_w(const uint8_t* p, uint32_t (&w)[BITS]) {
   }
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Weight staging: every thread copies exactly the bytes it will consume (its 32-k slice of rows r and r+8 of a step)
-// into its own shared-memory slot with cp.async, PF steps ahead.  In-flight HBM requests are then tracked by
-// cp.async groups instead of register scoreboards, so the L1-hit activation loads of the current step never wait
-// behind a DRAM round trip of a prefetch (the v1 register queue did: ~2 us per step, profiles/r1_v1_*).
-template <int BITS>
-__device__ __forceinline__ void stage_copy(uint32_t slot, const uint8_t* ga, const uint8_t* gb) {
-  if constexpr (BITS == 4) {
-    cp_async16(slot, ga);
-    cp_async16(slot + 512, gb);
-  } else {
-    cp_async8(slot, ga);
-    cp_async8(slot + 256, gb);
-  }
-}
-template <int BITS>
-__device__ __forceinline__ void stage_read(uint32_t slot, uint32_t (&wa)[BITS], uint32_t (&wb)[BITS]) {
-  if constexpr (BITS == 4) {
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wa[0]), "=r"(wa[1]), "=r"(wa[2]), "=r"(wa[3]) : "r"(slot));
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wb[0]), "=r"(wb[1]), "=r"(wb[2]), "=r"(wb[3]) : "r"(slot + 512));
-  } else {
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wa[0]), "=r"(wa[1]) : "r"(slot));
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wb[0]), "=r"(wb[1]) : "r"(slot + 256));
-  }
-}
-
 // split [0, total) into `parts` nearly equal contiguous ranges
 __device__ __forceinline__ void split_range(int total, int parts, int idx, int& begin, int& end) {
   const int base = total / parts, rem = total % parts;
@@ -558,15 +523,6 @@ __device__ __forceinline__ void sk_mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void sk_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sk_mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool sk_mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
 }
 __device__ __forceinline__ void sk_mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
