@@ -114,11 +114,10 @@ __device__ __forceinline__ void split_range(int total, int parts, int idx, int& 
 //   ZK: 0 no zeros (constant zero point of the "int" formats only), 1 "original", 2 "rescale", 3 "quantized"
 //   SC: with_scaling
 // ---------------------------------------------------------------------------------------------
-//   ST: (NT == 1, M <= 2, ZK in {0,3}) the CTA stages the activations A[M, K] and its 16 rows of group parameters in
-//       shared memory once, BEFORE the weight stream starts, and the main loop only issues ld.shared besides the weight
-//       prefetch.  Loads of one warp complete in order: an L1-hit ld.global issued behind the prefetch of the previous step
-//       waits a DRAM round trip every step (profiles/r1_gemv_*: long-scoreboard stalls on the first HMMA of every word).
-template <typename T, int BITS, bool IL, int NT, int ZK, bool SC, bool ST>
+// (A variant that staged the activations and the row block's group parameters in shared memory before the weight stream was
+// measured and removed: 39.2 us vs 30.7 us on 12288^2 -- the staging prologue of a short-lived CTA costs more than the in-order
+// load stalls it removes.)
+template <typename T, int BITS, bool IL, int NT, int ZK, bool SC>
 __global__ void __launch_bounds__(NT == 1 ? 128 : MAX_KS * 32)
 __maxnreg__(NT == 1 ? ((ZK == 1 || ZK == 2) ? 112 : 96) : (NT == 2 ? ((ZK == 1 || ZK == 2) ? 168 : 128) : ((ZK == 1 || ZK == 2) ? 232 : 192)))
 gemv_mma_kernel(const GemvParams p) {
@@ -186,11 +185,6 @@ gemv_mma_kernel(const GemvParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) asum_g[t][j] = 0.f;
 
-  extern __shared__ __align__(16) uint8_t st_smem[];
-  const uint32_t sA_base = (uint32_t)__cvta_generic_to_shared(st_smem);
-  const uint32_t sA_row_bytes = uint32_t(p.K) * 2;
-  const uint32_t sS_base = sA_base + uint32_t(ST ? p.M : 0) * sA_row_bytes;
-  const uint32_t sZ_base = sS_base + 16u * uint32_t(p.G) * 2u;
   // per-group state
   float s_a = 1.f, s_b = 1.f, zc_a = 0.f, zc_b = 0.f;
   uint32_t dzf[4] = {0u, 0u, 0u, 0u};  // -(z - rint(z)) fragment for non-integer "original" zero points
@@ -208,23 +202,6 @@ gemv_mma_kernel(const GemvParams p) {
   // group parameters are fetched one group ahead (raw bits) so their L2 latency overlaps a whole step
   uint16_t sr_a = 0, sr_b = 0, zr_a = 0, zr_b = 0;
   auto fetch_group = [&]() {
-    if constexpr (ST) {
-      const int g2 = p.G - groups_to_fetch;  // group index being fetched
-      if (groups_to_fetch > 0) {
-        if constexpr (SC) {
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sr_a) : "r"(sS_base + (r * p.G + g2) * 2));
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sr_b) : "r"(sS_base + ((r + 8) * p.G + g2) * 2));
-        }
-        if constexpr (ZK == 3) {
-          uint32_t za, zb;
-          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(za) : "r"(sZ_base + g2 * 8 + r / EPB));
-          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(zb) : "r"(sZ_base + g2 * 8 + (r + 8) / EPB));
-          zr_a = uint16_t(za); zr_b = uint16_t(zb);
-        }
-        --groups_to_fetch;
-      }
-      return;
-    }
     if (groups_to_fetch > 0) {
       if constexpr (SC) {
         sr_a = __ldg(sp_a);
@@ -306,46 +283,6 @@ gemv_mma_kernel(const GemvParams p) {
       ap[t] += 16;
     }
   };
-  // ---- ST: CTA-wide staging.  sA: per batch row, per 128-k step 256 B, pieces permuted so that the four q lanes of a
-  // quad read 64 contiguous bytes per ld.shared.v4 (piece (q, x) of a step lives at x*64 + q*16); sS: scales [16][G]
-  // (raw 16-bit); sZ: quantized zero bytes [G][8]
-  if constexpr (ST) {
-    const int nthr = blockDim.x, tid = threadIdx.x;
-    const uint4* Ag = reinterpret_cast<const uint4*>(p.A);
-    const int pieces_per_row = p.K / 8;  // 16-byte pieces
-    for (int pid = tid; pid < p.M * pieces_per_row; pid += nthr) {
-      const int m = pid / pieces_per_row, pr = pid % pieces_per_row, pp = pr & 15;
-      const uint4 v = __ldg(Ag + pid);
-      const uint32_t dst = sA_base + m * sA_row_bytes + (pr >> 4) * 256 + (pp & 3) * 64 + (pp >> 2) * 16;
-      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
-    }
-    if constexpr (SC) {
-      const uint16_t* sg = reinterpret_cast<const uint16_t*>(p.scale) + size_t(rb) * 16 * p.G;  // 16 consecutive rows
-      for (int i = tid; i < 16 * p.G; i += nthr) {
-        const uint16_t v = __ldg(sg + i);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sS_base + i * 2), "h"(v));
-      }
-    }
-    if constexpr (ZK == 3) {
-      const uint8_t* zg = reinterpret_cast<const uint8_t*>(p.zeros) + size_t(rb) * 16 / EPB;
-      const int bpg = 16 / EPB;  // zero bytes per group for this row block
-      for (int i = tid; i < p.G * bpg; i += nthr) {
-        const int g2 = i / bpg, b = i % bpg;
-        const uint32_t v = __ldg(zg + size_t(g2) * qz_stride + b);
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(sZ_base + g2 * 8 + b), "r"(v));
-      }
-    }
-    __syncthreads();
-  }
-  const uint32_t sA_read = sA_base + min(r, max(p.M, 1) - 1) * sA_row_bytes + uint32_t(step_begin) * 256 + q * 16;
-  auto read_acts = [&](int step_local, uint32_t (&dst)[NT][RPS]) {
-    const uint32_t a = sA_read + step_local * 256;
-#pragma unroll
-    for (int x = 0; x < RPS / 4; ++x)
-      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(dst[0][4 * x]), "=r"(dst[0][4 * x + 1]), "=r"(dst[0][4 * x + 2]), "=r"(dst[0][4 * x + 3])
-                   : "r"(a + x * 64));
-  };
   auto process = [&](const uint32_t (&wa)[WPS], const uint32_t (&wb)[WPS], const uint32_t (&Rc)[NT][RPS]) {
     if (grp_left == 0) {
       end_group();
@@ -417,7 +354,7 @@ gemv_mma_kernel(const GemvParams p) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         if (!GUARD || s + u < ns) {
-          if constexpr (ST) read_acts(s + u, Rbuf[0]); else load_acts(Rbuf[0]);
+          load_acts(Rbuf[0]);
           process(wq[u][0], wq[u][1], Rbuf[0]);
           if (!GUARD || s + u + PF < ns) { load_w<BITS>(wnext_a, wq[u][0]); load_w<BITS>(wnext_b, wq[u][1]); }
           wnext_a += STEP_BYTES; wnext_b += STEP_BYTES;
@@ -1224,15 +1161,11 @@ template <typename T, int BITS, bool IL>
 int launch_mma_nt(const MatmulArgs& a, GemvParams p) {
   const int nb = p.N / 16;
   const int nt = (p.M + 7) / 8;
-  // The CTA-staged variant (ST = true: activations + group parameters in shared memory before the weight stream starts) is
-  // kept in the kernel source but not instantiated: on B200 it measured SLOWER than loading the activations with
-  // ld.global at use (12288^2, m=1: 39.2 us vs 30.7 us; 4-shape step 157 us vs 133 us) -- the staging prologue and the
-  // shared-memory footprint cost more than the in-order load stalls they remove.
   const int stage_bytes = 0;
 #define BB_GEMV_NT(ZKV, SCV)                                                             \
-  if (nt <= 1) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV, SCV, false>), 4) \
-  else if (nt == 2) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 2, ZKV, SCV, false>), MAX_KS) \
-  else BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 4, ZKV, SCV, false>), MAX_KS)
+  if (nt <= 1) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 1, ZKV, SCV>), 4) \
+  else if (nt == 2) BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 2, ZKV, SCV>), MAX_KS) \
+  else BB_GEMV_GO((gemv_mma_kernel<T, BITS, IL, 4, ZKV, SCV>), MAX_KS)
   if (!p.with_scaling) { BB_GEMV_NT(0, false) }
   else if (p.zmode == 0) { BB_GEMV_NT(0, true) }
   else if (p.zmode == 1) { BB_GEMV_NT(1, true) }
