@@ -18,7 +18,7 @@ BB_W_UINT, BB_W_INT, BB_W_NF, BB_W_FP4, BB_W_FP8_E4M3, BB_W_FP8_E5M2 = 0, 1, 2, 
 BB_ZEROS_ORIGINAL, BB_ZEROS_RESCALE, BB_ZEROS_QUANTIZED = 0, 1, 2
 BB_LAYOUT_COMPRESSED, BB_LAYOUT_INTERLEAVED_16, BB_LAYOUT_INTERLEAVED_8 = 0, 1, 2
 (BB_KERNEL_AUTO, BB_KERNEL_GENERIC, BB_KERNEL_GEMV_MMA, BB_KERNEL_GEMV_I8, BB_KERNEL_GEMM_TS,
- BB_KERNEL_GEMM_TS_I8, BB_KERNEL_GEMV_STREAMK) = range(7)
+ BB_KERNEL_GEMM_TS_I8, BB_KERNEL_GEMV_STREAMK, BB_KERNEL_GEMV_SLAB) = range(8)
 
 DTYPE_IDS = {"float16": BB_F16, "bfloat16": BB_BF16, "float32": BB_F32, "int8": BB_I8, "int32": BB_I32}
 WFMT_IDS = {"uint": BB_W_UINT, "int": BB_W_INT, "nf": BB_W_NF, "fp": BB_W_FP4, "fp_e4m3": BB_W_FP8_E4M3,
@@ -29,7 +29,7 @@ EXPORTS = [
     "bb_init", "bb_matmul", "bb_matmul_scatter", "bb_workspace_bytes", "bb_select_kernel", "bb_kernel_name", "bb_set_kernel_override",
     "bb_launch_count", "bb_last_error", "bb_version", "bb_compress_host", "bb_interleave_host",
     "bb_transform_weight_device", "bb_repack_gptq_qweight_device", "bb_repack_gptq_qzeros_device",
-    "bb_debug_decode",
+    "bb_debug_decode", "bb_debug_dequant",
 ]
 
 
@@ -44,6 +44,7 @@ class MatmulDesc(ctypes.Structure):
 
 
 _lib = None
+OVERRIDE_GEN = 0   # bumped by every bb_set_kernel_override call (testing hook)
 
 
 def load() -> ctypes.CDLL:
@@ -65,6 +66,13 @@ def load() -> ctypes.CDLL:
     lib.bb_select_kernel.argtypes = [dp, i32]; lib.bb_select_kernel.restype = i32
     lib.bb_kernel_name.argtypes = [i32]; lib.bb_kernel_name.restype = ctypes.c_char_p
     lib.bb_set_kernel_override.argtypes = [i32]; lib.bb_set_kernel_override.restype = i32
+    _c_override = lib.bb_set_kernel_override
+
+    def _set_override(kernel_id):   # operators cache bb_workspace_bytes per (m, override generation)
+        global OVERRIDE_GEN
+        OVERRIDE_GEN += 1
+        return _c_override(int(kernel_id))
+    lib.bb_set_kernel_override = _set_override
     lib.bb_launch_count.argtypes = []; lib.bb_launch_count.restype = ctypes.c_uint64
     lib.bb_last_error.argtypes = []; lib.bb_last_error.restype = ctypes.c_char_p
     lib.bb_version.argtypes = []; lib.bb_version.restype = i32
@@ -74,6 +82,7 @@ def load() -> ctypes.CDLL:
     lib.bb_repack_gptq_qweight_device.argtypes = [vp, vp, i64, i64, i32, i32, vp]; lib.bb_repack_gptq_qweight_device.restype = i32
     lib.bb_repack_gptq_qzeros_device.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]; lib.bb_repack_gptq_qzeros_device.restype = i32
     lib.bb_debug_decode.argtypes = [i32, i32, i32, i32, vp, vp, i32, vp]; lib.bb_debug_decode.restype = i32
+    lib.bb_debug_dequant.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]; lib.bb_debug_dequant.restype = i32
     _lib = lib
     return lib
 

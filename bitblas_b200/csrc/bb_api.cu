@@ -16,7 +16,7 @@ namespace bb {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_override{BB_KERNEL_AUTO};
-static int g_sm_count = 0;
+static std::atomic<int> g_sm_count[BB_MAX_DEVICES];   // 0 = not queried yet; per-device state is keyed on the ordinal
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -25,16 +25,20 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return (dev < 0 || dev >= BB_MAX_DEVICES) ? 0 : dev;
+}
+
 int device_sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_sm_count = n;
-    else
-      g_sm_count = 148;
+  const int dev = current_device();
+  int n = g_sm_count[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    g_sm_count[dev].store(n, std::memory_order_relaxed);
   }
-  return g_sm_count;
+  return n;
 }
 
 static int validate(const bb_matmul_desc* d) {
@@ -74,12 +78,14 @@ static int select(const bb_matmul_desc& d, int m) {
       case BB_KERNEL_GEMM_TS: if (d.a_dtype != BB_I8 && gemm_ts_supported(d, m)) return ov; break;
       case BB_KERNEL_GEMM_TS_I8: if (d.a_dtype == BB_I8 && gemm_ts_supported(d, m)) return ov; break;
       case BB_KERNEL_GEMV_STREAMK: if (gemv_streamk_supported(d, m)) return ov; break;
+      case BB_KERNEL_GEMV_SLAB: if (gemv_slab_supported(d, m)) return ov; break;
     }
     return -1;
   }
   // m <= 8 (one n8 MMA tile): streaming kernels; above that the tcgen05 kernel (split-K keeps the SMs busy at small m)
   // is faster (12288^2 sweep, tools/smallm_sweep.py); the streaming kernels stay as the fallback up to m = 32.
   if (m <= 8) {
+    if (gemv_slab_supported(d, m)) return BB_KERNEL_GEMV_SLAB;
     if (gemv_mma_supported(d, m)) return BB_KERNEL_GEMV_MMA;
     if (gemv_i8_supported(d, m)) return BB_KERNEL_GEMV_I8;
   }
@@ -111,12 +117,13 @@ int bb_init(int device) {
     return 2;
   }
   if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return 1; }
-  BB_CHECK_CUDA(cudaSetDevice(device));
+  // queries only: the caller's current device is left untouched (torch owns it)
   int major = 0;
   BB_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
   if (major != 10) { set_error("bitblas_b200 needs an sm_100a device (compute capability 10.x), found %d.x", major); return 2; }
-  g_sm_count = 0;
-  device_sm_count();
+  int n = 0;
+  BB_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+  if (device < BB_MAX_DEVICES && n > 0) g_sm_count[device].store(n);
   return gemm_ts_init(device);
 }
 
@@ -134,6 +141,7 @@ const char* bb_kernel_name(int id) {
     case BB_KERNEL_GEMM_TS: return "gemm_ts_tcgen05";
     case BB_KERNEL_GEMM_TS_I8: return "gemm_ts_tcgen05_i8";
     case BB_KERNEL_GEMV_STREAMK: return "gemv_streamk";
+    case BB_KERNEL_GEMV_SLAB: return "gemv_slab";
   }
   return "unknown";
 }
@@ -145,6 +153,7 @@ size_t bb_workspace_bytes(const bb_matmul_desc* desc, int m) {
   const int k = select(*desc, m);
   if (k == BB_KERNEL_GEMM_TS || k == BB_KERNEL_GEMM_TS_I8) return gemm_ts_workspace_bytes(*desc, m);
   if (k == BB_KERNEL_GEMV_STREAMK) return gemv_streamk_workspace_bytes();
+  if (k == BB_KERNEL_GEMV_SLAB) return gemv_slab_workspace_bytes();
   return 0;
 }
 
@@ -180,6 +189,7 @@ static int matmul_impl(const bb_matmul_desc* desc, const void* A, const void* W,
     case BB_KERNEL_GEMV_MMA: return launch_gemv_mma(a);
     case BB_KERNEL_GEMV_I8: return launch_gemv_i8(a);
     case BB_KERNEL_GEMV_STREAMK: return launch_gemv_streamk(a);
+    case BB_KERNEL_GEMV_SLAB: return launch_gemv_slab(a);
     case BB_KERNEL_GEMM_TS:
     case BB_KERNEL_GEMM_TS_I8: return launch_gemm_ts(a);
   }

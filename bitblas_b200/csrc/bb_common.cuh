@@ -58,7 +58,9 @@ struct MatmulArgs {
   int gsize() const { return d.group_size <= 0 ? d.K : d.group_size; }
 };
 
-int device_sm_count();
+constexpr int BB_MAX_DEVICES = 64;
+int current_device();     // ordinal of the calling thread's current CUDA device, clamped to [0, BB_MAX_DEVICES)
+int device_sm_count();    // SM count of the current device (cached per device)
 
 // kernel family entry points (each returns 0 / error code; *_supported says whether the family covers it)
 bool generic_supported(const bb_matmul_desc& d);
@@ -68,6 +70,9 @@ int launch_gemv_mma(const MatmulArgs& a);
 bool gemv_streamk_supported(const bb_matmul_desc& d, int m);
 int launch_gemv_streamk(const MatmulArgs& a);
 size_t gemv_streamk_workspace_bytes();  // partial slots + flags
+bool gemv_slab_supported(const bb_matmul_desc& d, int m);
+int launch_gemv_slab(const MatmulArgs& a);
+size_t gemv_slab_workspace_bytes();     // tagged partial slots (must be zero-initialised once by the caller)
 bool gemv_i8_supported(const bb_matmul_desc& d, int m);
 int launch_gemv_i8(const MatmulArgs& a);
 bool gemm_ts_supported(const bb_matmul_desc& d, int m);
@@ -197,6 +202,23 @@ template <typename T>
 __device__ __forceinline__ uint32_t dup2(T v) {
   uint16_t b = *reinterpret_cast<uint16_t*>(&v);
   return (uint32_t(b) << 16) | b;
+}
+
+// Per-group dequant constants (one weight row) of the tensor-core GEMM path:  v = ((x - mz) [- z2]) * s2 [+ negz2]
+struct DqConst {
+  uint32_t mz_lo, mz_hi;  // decode magic + folded integer zero point, for even / odd nibble positions
+  uint32_t z2, s2, negz2;
+};
+// raw "magic + u" pair -> dequantised A_dtype pair, in A_dtype arithmetic with the reference's rounding order
+// (bitblas/gpu/intrin/lop3.py:172-175 sub then mul; :256,269 rescale = one fma).  MODE: 0 none, 1 scale, 2 "original"
+// zeros, 3 "rescale" zeros, 4 quantized zeros (integer zero point folded into mz).
+template <typename T, int MODE>
+__device__ __forceinline__ uint32_t dq_finish(uint32_t x, uint32_t mz, const DqConst& c) {
+  const uint32_t t = sub2<T>(x, mz);
+  if constexpr (MODE == 1 || MODE == 4) return mul2<T>(t, c.s2);
+  if constexpr (MODE == 2) return mul2<T>(sub2<T>(t, c.z2), c.s2);
+  if constexpr (MODE == 3) return fma2<T>(t, c.s2, c.negz2);
+  return t;
 }
 
 // ---- in-register decode of packed low-bit words -----------------------------------------------

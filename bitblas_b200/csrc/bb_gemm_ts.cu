@@ -216,12 +216,6 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   return v;
 }
 
-// Per-group dequant constants (one weight row):  v = ((x - mz) [- z2]) * s2 [+ negz2]
-struct DqConst {
-  uint32_t mz_lo, mz_hi;  // decode magic + folded integer zero point, for even / odd nibble positions
-  uint32_t z2, s2, negz2;
-};
-
 // decode this thread's half of the k-block (PRB/2 packed bytes at shared address `src`) into 16 registers of
 // natural-k-order 16-bit operand pairs.  MODE: 0 none, 1 scale, 2 original, 3 rescale, 4 quantized.
 // IL = LOP3-interleaved storage (fast_decoding); !IL = plain compressed storage, re-ordered with byte permutes.
@@ -229,14 +223,7 @@ template <typename T, int BITS, int MODE, bool IL>
 __device__ __forceinline__ void dequant_half_row(uint32_t src, uint32_t (&out)[16], const DqConst& c) {
   constexpr bool HI = IL && std::is_same<T, __half>::value && BITS == 4;
   constexpr uint32_t M = TypeTraits<T>::kMagic;
-  auto fin = [&](uint32_t x, uint32_t mz) -> uint32_t {
-    uint32_t t = sub2<T>(x, mz);
-    if constexpr (MODE == 0) return t;
-    if constexpr (MODE == 1 || MODE == 4) return mul2<T>(t, c.s2);
-    if constexpr (MODE == 2) return mul2<T>(sub2<T>(t, c.z2), c.s2);
-    if constexpr (MODE == 3) return fma2<T>(t, c.s2, c.negz2);
-    return t;
-  };
+  auto fin = [&](uint32_t x, uint32_t mz) -> uint32_t { return dq_finish<T, MODE>(x, mz, c); };
   if constexpr (BITS == 4) {
     const uint4 pk = lds128(src);
     const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
@@ -477,7 +464,6 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       int gi = (kb0 + grp) / kb_per_g;         // group of this warp's first k-block
       int g_end = (gi + 1) * kb_per_g - kb0;   // first (CTA-local) k-block of the next group
-      const int g_step = kb_per_g >= DQ_GROUPS ? 1 : DQ_GROUPS / kb_per_g;  // groups skipped per switch
       bool fresh = true;
       if constexpr (MODE != 0) fetch_group(gi);
       int st = grp;                      // smem stage of kb (S % DQ_GROUPS == 0 keeps stage parity per group)
@@ -503,7 +489,11 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               c.mz_lo = MAGIC + zq * 0x00010001u;
               c.mz_hi = MAGIC_HI + (zq * ZSH) * 0x00010001u;
             }
-            if (gi + g_step < p.G) fetch_group(gi + g_step);
+            // prefetch the parameters of the group this warp enters next: its first own k-block at or past g_end (the
+            // stride DQ_GROUPS need not divide the group length -- g = 192 with four dequant groups skips 1 or 2 groups)
+            const int kbn = kb + ((g_end - kb + DQ_GROUPS - 1) / DQ_GROUPS) * DQ_GROUPS;
+            const int gn = gi + 1 + (kbn - g_end) / kb_per_g;
+            if (kbn < num_kb && gn < p.G) fetch_group(gn);
           }
         }
         // The previous k-block's slot is normally published AFTER this block's first decode (its tcgen05.st hides behind
@@ -769,10 +759,11 @@ int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
   using SM = TsSmem<T, BITS, BM>;
   using EI = ElemInfo<T>;
   auto kernel = gemm_ts_kernel<T, BITS, BM, IL>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[BB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     BB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   TsParams p = p0;
   p.m_tiles = (a.m + BM - 1) / BM;

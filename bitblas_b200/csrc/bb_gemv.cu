@@ -1000,7 +1000,8 @@ GemvParams make_params(const MatmulArgs& a) {
 template <typename KernelT>
 int pick_ks(KernelT kernel, int (&occ_cache)[MAX_KS + 1], int max_ks, int row_blocks, int steps, int stage_bytes) {
   const int sms = device_sm_count();
-  static const int ks_env = [] { const char* e = getenv("BB_GEMV_KS"); return e ? atoi(e) : 0; }();   // tuning hook
+  const char* ks_e = getenv("BB_GEMV_KS");   // tuning / test hook, read per launch
+  const int ks_env = ks_e ? atoi(ks_e) : 0;
   if (ks_env >= 1 && ks_env <= max_ks && ks_env <= steps) return ks_env;
   for (int ks = max_ks; ks >= 2; --ks) {
     if (ks > steps) continue;
@@ -1050,10 +1051,7 @@ SkEncodeFn sk_encode() {
   return fn;
 }
 
-int sk_sm_count() {
-  static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
-  return sms;
-}
+int sk_sm_count() { return device_sm_count(); }
 constexpr int SK_MAX_MINB = 4;   // CTAs per SM of the densest variant (sizes the workspace)
 size_t sk_workspace_bytes() { return size_t(SK_MAX_MINB * sk_sm_count() * SK_CONSUMERS) * (SK_SLOT_FLOATS * 4 + 8) + 256; }
 
@@ -1122,7 +1120,8 @@ int launch_gemv_sk(const MatmulArgs& a, const GemvParams& p) {
 #define BB_SK_GO2(ZKV, GPCV, MB)                                                                                            \
   {                                                                                                                \
     auto k = gemv_sk_kernel<T, IL, ZKV, GPCV, MB>;                                                                 \
-    static int occ[SK_MAX_M + 1] = {0};                                                                            \
+    static int occ_dev[BB_MAX_DEVICES][SK_MAX_M + 1] = {};   /* cudaFuncSetAttribute is per device */           \
+    int (&occ)[SK_MAX_M + 1] = occ_dev[current_device()];                                                         \
     if (!occ[p.M]) {                                                                                               \
       BB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(SK_MAX_M, SK_DEPTH))); \
       int o = 0;                                                                                                   \

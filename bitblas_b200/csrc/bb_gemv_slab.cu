@@ -1,0 +1,623 @@
+// bb_gemv_slab.cu -- m = 1 decode GEMV, W4A16 (fp16 / bf16 activations x 4-bit weights), the HBM-bound headline kernel.
+//
+// Replaces the reference's generated SIMT GEMV (bitblas/ops/general_matmul/tilelang/dequantize/gemv_dequantize_simt.py:164-262)
+// and supersedes the round-1 register-queue kernel (bb_gemv.cu: 0.40 of the HBM roofline, bound by instruction issue and by
+// DRAM round trips sitting on the warps' scoreboards).  Design, top down:
+//
+//   * WORK UNIT = [16 weight rows] x [2048 k] = 16 KB of packed weights out of the unchanged [N, K/2] storage, fetched as 16
+//     bulk copies (cp.async.bulk, UBLKCP) of one row's contiguous 1 KB each -- a DRAM page activation serves 1 KB instead of
+//     64-128 B.  (Measured, profiles/r2_slab_*: the TMA engine moves one box ROW per request step, so a tensor-map box with
+//     128-byte rows -- the swizzled layout a GEMM would use -- streams DRAM at only ~1.2 TB/s from two issuing CTAs per SM;
+//     1 KB rows reach the linear-read rate.)  The rows land in shared memory at a pitch of 1024 + 16 bytes, which makes the
+//     consumers' 128-bit reads conflict-free without a swizzle.  Units are ordered row block by row block and cut into equal
+//     contiguous ranges over a persistent grid (CTA-level stream-K): every SM streams the same number of bytes whatever N, K
+//     are; a 1024-row tensor-parallel shard still fills all 148 SMs.
+//   * a CTA = 8 consumer warps + a loader warp + a parameter-converter warp around an S-stage mbarrier ring in shared memory.  The consumers issue NO
+//     global loads: weights, activations, group parameters and activation group sums are all in the stage when its barrier
+//     flips, so nothing but ld.shared latency ever sits on a consumer scoreboard.
+//   * consumer warp w owns K-slice w of the unit (16 rows x 128 B = two 128-k steps): ld.shared.v4 -> LOP3 decode into
+//     mma.sync.m16n8k16 A fragments (fp16: even nibbles as 1024+u, odd nibbles in place as 64+u) -> 8 HMMA per step with the
+//     activations as the n8 side.  The decode magic and the zero point are never subtracted per element and never folded
+//     through extra MMAs (round 1 spent half its HMMAs on that): per step
+//         acc += c1[row] * (partial - SM) + c2[row] * S,    SM = sum_k magic(k) a[k],  S = sum_k a[k]   (per 128-k step)
+//     with (c1, c2) = (s, -s*z) for "original" / quantized zeros, (s, -z) for "rescale", (s, -s*2^(b-1)) for int formats.
+//     This is exact in fp32 for ANY zero point (no integer / fraction split) and is three FMAs per output row per step.
+//   * the loader warp issues the unit's 16 weight-row copies + the activation slab copy; the converter warp fetches the unit's
+//     scales / zeros with plain loads one unit ahead and writes them as fp32 (c1, c2) pairs; (SM, S) for every 128-k step of K
+//     are computed once per CTA by all threads before the stream starts (while the first ring-full of weights is in flight).
+//     (First version, profiles/r2_slab_v0_*: ONE producer warp doing all of that per unit -- ~900 instructions -- capped a
+//     CTA at one unit per ~6000 cycles, 1.6 TB/s chip-wide whatever the ring depth.)
+//   * stream-K fix-up: a range that starts inside a row block parks its CTA-reduced partial row sums in tagged 64-bit
+//     workspace slots {call nonce, fp32}; the range holding the block's first unit adds them in fixed order (bit-reproducible)
+//     and stores.  Ranges are handed out in reverse CTA order so an owner only waits for CTAs dispatched before it.
+//   * programmatic dependent launch: weights of the first S units are requested before griddepcontrol.wait, activations
+//     after it; launch_dependents is raised at kernel entry -- the grid is persistent and fully resident, so the next
+//     kernel's CTAs can only take slots that this kernel's CTAs have vacated, and its weight prefetch overlaps our tail.
+#include <atomic>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "bb_common.cuh"
+
+namespace bb {
+
+namespace {
+
+constexpr int GS_NCONS = 8;                         // consumer warps per CTA = K-slices per unit
+constexpr int GS_THREADS = (GS_NCONS + 2) * 32;     // + loader warp + parameter converter warp
+constexpr int GS_SLICE_BYTES = 128;                 // packed bytes per row per consumer per unit
+constexpr int GS_KU = GS_NCONS * GS_SLICE_BYTES * 2;   // k per unit (4-bit): 2048
+constexpr int GS_STEPS = GS_KU / 128;               // 128-k steps per unit: 16
+constexpr int GS_ROW_BYTES = GS_SLICE_BYTES * GS_NCONS;     // packed bytes per row per unit: 1 KB, one bulk copy
+constexpr int GS_ROW_PITCH = GS_ROW_BYTES + 16;             // shared-memory pitch of a slab row: the 16 B skew makes rows i and i+4
+                                                            // (the two rows met by one ld.shared.v4 phase) 64 B apart in bank space
+constexpr int GS_WBYTES = 16 * GS_ROW_PITCH + 256;          // 16.5 KB
+constexpr int GS_ABYTES = GS_KU * 2;                // activation slab (one batch row)
+constexpr int GS_PBYTES = GS_STEPS * 16 * 8;        // (c1, c2) fp32 pairs [step][row]
+constexpr int GS_STAGE_BYTES = GS_WBYTES + GS_ABYTES + GS_PBYTES;
+constexpr int GS_RED_BYTES = 2 * GS_NCONS * 16 * 4;
+constexpr int GS_MAX_STAGES = 6;
+constexpr int GS_MAX_CPS = 3;
+
+struct SlabParams {
+  const void* A;
+  const void* scale;
+  const void* zeros;
+  const void* bias;
+  OutSpec out;
+  int N, K;
+  int G;            // groups per row
+  int g128;         // group size / 128
+  int with_scaling;
+  int zmode;        // 0 none, 1 original, 2 rescale, 3 quantized
+  int zp_const;
+  int out_dtype;
+  int UPR;          // units per 16-row block
+  int T;            // units in total
+  int stages;
+  const uint8_t* W;
+  unsigned long long* ws;   // [grid][16] tagged partial slots, zero-tagged on entry and on exit
+  unsigned int nonce;
+  int vec_scale;    // scales of 8 consecutive groups can be fetched with one aligned 16-byte load
+};
+
+__device__ __forceinline__ uint32_t gs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gs_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void gs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gs_mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {   // no arrival
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gs_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gs_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GS_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GS_DONE_%=;\n"
+      "bra GS_WAIT_%=;\n"
+      "GS_DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void gs_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint4 gs_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 gs_lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void gs_sts64f(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void gs_sts32f(uint32_t addr, float a) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
+__device__ __forceinline__ float gs_lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void gs_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void gs_mma<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void gs_mma<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T>
+__device__ __forceinline__ float gs_raw_to_float(uint32_t b) {
+  const uint16_t h = uint16_t(b);
+  return TypeTraits<T>::to_float(*reinterpret_cast<const T*>(&h));
+}
+
+template <typename T>
+__device__ __forceinline__ void gs_store(const SlabParams& p, int n, float v) {
+  const size_t o = size_t(p.out.col0) + n;   // m == 0
+  const float bf = p.bias ? TypeTraits<T>::to_float(reinterpret_cast<const T*>(p.bias)[n]) : 0.f;
+  if (p.out_dtype == BB_F16) {
+    __half h = __float2half_rn(v);
+    if (p.bias) h = __hadd(h, __float2half_rn(bf));
+    for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__half*>(p.out.ptr[d])[o] = h;
+  } else if (p.out_dtype == BB_BF16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    if (p.bias) h = __hadd(h, __float2bfloat16_rn(bf));
+    for (int d = 0; d < p.out.n; ++d) reinterpret_cast<__nv_bfloat16*>(p.out.ptr[d])[o] = h;
+  } else {
+    for (int d = 0; d < p.out.n; ++d) reinterpret_cast<float*>(p.out.ptr[d])[o] = v + bf;
+  }
+}
+
+__device__ __forceinline__ int gs_range_begin(int ri, int T, int R) { return int((long long)ri * T / R); }
+
+template <typename T, bool IL, int CPS>
+__global__ void __launch_bounds__(GS_THREADS, CPS)
+gemv_slab_kernel(const SlabParams p) {
+  constexpr bool F16 = std::is_same<T, __half>::value;
+  constexpr bool HI = F16;   // odd nibbles decoded in place (mantissa bits 4..7 under exponent 2^6: exactly 64 + u)
+  constexpr uint32_t MAGIC = TypeTraits<T>::kMagic;
+  constexpr uint32_t MAGIC_HI = 0x54005400u;
+  extern __shared__ uint8_t gs_raw[];
+  const int S = p.stages;
+  const uint32_t base = (gs_smem_u32(gs_raw) + 1023u) & ~1023u;
+  const uint32_t Wb = base;
+  const uint32_t Ab = Wb + uint32_t(S) * GS_WBYTES;
+  const uint32_t Pb = Ab + uint32_t(S) * GS_ABYTES;
+  const uint32_t Rb = Pb + uint32_t(S) * GS_PBYTES;
+  const uint32_t Bb = Rb + GS_RED_BYTES;               // full[S], empty[S]
+  const uint32_t SUMb = Bb + 16u * uint32_t(GS_MAX_STAGES);   // (SM, S) fp32 pairs for every 128-k step of K
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      gs_mbar_init(Bb + 8u * s, 2);             // full: loader (arrive.expect_tx of the copies) + converter (parameters written)
+      gs_mbar_init(Bb + 8u * (S + s), GS_NCONS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int R = gridDim.x;
+  const int ri = R - 1 - int(blockIdx.x);   // ranges in reverse CTA order: an owner waits only for CTAs dispatched before it
+  const int t0 = gs_range_begin(ri, p.T, R), t1 = gs_range_begin(ri + 1, p.T, R);
+  const int n_units = t1 - t0;
+  const int UPR = p.UPR;
+  const int Kb = p.K >> 1;                  // packed bytes per row
+  const int steps_total = p.K >> 7;         // 128-k steps per row
+  const int rb0 = t0 / UPR, ku0 = t0 - rb0 * UPR;
+  const int npre = min(S, n_units);
+
+  // weights of one unit: 16 bulk copies of one row's (up to) 1 KB each, issued by lanes 0..15, into the skewed slab
+  auto issue_w = [&](int rb, int ku, int slot) {
+    const uint32_t nb = uint32_t(min(GS_ROW_BYTES, Kb - ku * GS_ROW_BYTES));
+    if (lane < 16)
+      gs_bulk_g2s(Wb + uint32_t(slot) * GS_WBYTES + uint32_t(lane) * GS_ROW_PITCH,
+                  p.W + size_t(rb * 16 + lane) * size_t(Kb) + size_t(ku) * GS_ROW_BYTES, nb, Bb + 8u * slot);
+  };
+  if (warp == GS_NCONS) {
+    // weights do not depend on the preceding kernel: request the first ring-full before waiting for it
+    int rbp = rb0, kup = ku0;
+    for (int u = 0; u < npre; ++u) {
+      if (lane == 0) gs_mbar_expect_tx_only(Bb + 8u * u, 16u * uint32_t(min(GS_ROW_BYTES, Kb - kup * GS_ROW_BYTES)));
+      __syncwarp();
+      issue_w(rbp, kup, u);
+      if (++kup == UPR) { kup = 0; ++rbp; }
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // activations (and our stores) depend on the preceding kernel
+
+  // ---- activation sums per 128-k step, once per CTA: S = sum a[k], SM = sum magic(k mod 8) a[k] (all threads) ----
+  {
+    const uint4* A4 = reinterpret_cast<const uint4*>(p.A);
+    const int nchunks = p.K >> 3;   // 16-byte chunks of 8 activations = the 8 elements of one packed weight word
+    for (int c = int(threadIdx.x); c < nchunks; c += GS_THREADS) {   // nchunks % 32 == 0: whole warps in or out
+      const uint4 v = __ldg(A4 + c);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        e[2 * i] = gs_raw_to_float<T>(w4[i] & 0xffffu);
+        e[2 * i + 1] = gs_raw_to_float<T>(w4[i] >> 16);
+      }
+      float s_all = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+      float sm;
+      if constexpr (!HI) sm = float(TypeTraits<T>::kMagicVal) * s_all;
+      else {
+        // elements decoded from odd nibble positions carry the magic 64 instead of 1024
+        const float s_hi = IL ? ((e[2] + e[3]) + (e[6] + e[7])) : ((e[1] + e[3]) + (e[5] + e[7]));
+        sm = 1024.f * (s_all - s_hi) + 64.f * s_hi;
+      }
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        s_all += __shfl_xor_sync(0xffffffffu, s_all, o);
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      }
+      if ((lane & 15) == 0) gs_sts64f(SUMb + uint32_t(c >> 4) * 8u, sm, s_all);
+    }
+  }
+  __syncthreads();
+
+  if (warp == GS_NCONS) {
+    // =========================== loader warp: one unit = 16 weight-row copies + the activation slab ===========================
+    int slot = 0, rb = rb0, ku = ku0;
+    uint32_t ephase = 1u;   // parity trick: the first pass over the ring finds every slot free
+#pragma unroll 1
+    for (int i = 0; i < n_units; ++i) {
+      gs_mbar_wait(Bb + 8u * (S + slot), ephase);
+      const int k0 = ku * GS_KU;
+      const uint32_t abytes = uint32_t(min(GS_KU, p.K - k0)) * 2u;
+      const uint32_t wbytes = 16u * uint32_t(min(GS_ROW_BYTES, Kb - ku * GS_ROW_BYTES));
+      if (lane == 0) gs_mbar_expect_tx(Bb + 8u * slot, abytes + (i >= npre ? wbytes : 0u));
+      __syncwarp();
+      if (i >= npre) issue_w(rb, ku, slot);
+      if (lane == 16)
+        gs_bulk_g2s(Ab + uint32_t(slot) * GS_ABYTES, reinterpret_cast<const uint8_t*>(p.A) + size_t(k0) * 2, abytes, Bb + 8u * slot);
+      if (++slot == S) { slot = 0; ephase ^= 1u; }
+      if (++ku == UPR) { ku = 0; ++rb; }
+    }
+    return;
+  }
+
+  if (warp == GS_NCONS + 1) {
+    // =========================== converter warp: scales / zeros of a unit -> fp32 (c1, c2) pairs [step][row] ===========================
+    // lane = (row, half of the unit's 16 steps).  Raw values are loaded one unit ahead (the loop is unrolled by two so that no
+    // register copy ever waits for the loads just issued) and converted when the ring slot is free.
+    const int prow = lane & 15, phalf = lane >> 4;
+    const uint16_t* scale16 = reinterpret_cast<const uint16_t*>(p.scale);
+    const uint16_t* zeros16 = reinterpret_cast<const uint16_t*>(p.zeros);
+    const uint8_t* zeros8 = reinterpret_cast<const uint8_t*>(p.zeros);
+    const bool vec_scale = p.vec_scale != 0;   // 8 consecutive groups = one aligned 16-byte load
+    uint32_t sA[8], zA[8], sB[8], zB[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sA[i] = zA[i] = sB[i] = zB[i] = 0u; }
+    int slot = 0, rb = rb0, ku = ku0;
+    uint32_t ephase = 1u;
+    auto fetch = [&](uint32_t (&sc)[8], uint32_t (&zc)[8]) {   // raw parameters of unit (rb, ku); advances (rb, ku)
+      const int n = rb * 16 + prow;
+      const int kstep = ku * GS_STEPS + phalf * 8;
+      int gi = kstep / p.g128, rem = kstep - gi * p.g128;
+      if (vec_scale) {
+        if (kstep < steps_total) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(scale16 + size_t(n) * p.G + gi));
+          sc[0] = v.x & 0xffffu; sc[1] = v.x >> 16; sc[2] = v.y & 0xffffu; sc[3] = v.y >> 16;
+          sc[4] = v.z & 0xffffu; sc[5] = v.z >> 16; sc[6] = v.w & 0xffffu; sc[7] = v.w >> 16;
+        }
+      }
+#pragma unroll
+      for (int st = 0; st < 8; ++st) {
+        if (kstep + st < steps_total) {
+          if (p.with_scaling && !vec_scale) sc[st] = __ldg(scale16 + size_t(n) * p.G + gi);
+          if (p.zmode == 1 || p.zmode == 2) zc[st] = __ldg(zeros16 + size_t(n) * p.G + gi);
+          else if (p.zmode == 3) zc[st] = __ldg(zeros8 + size_t(gi) * (p.N >> 1) + (n >> 1));   // nibble picked when consumed
+        }
+        if (++rem == p.g128) { rem = 0; ++gi; }
+      }
+      if (++ku == UPR) { ku = 0; ++rb; }
+    };
+    auto convert = [&](const uint32_t (&sp)[8], const uint32_t (&zp)[8]) {
+      gs_mbar_wait(Bb + 8u * (S + slot), ephase);
+      const uint32_t pbase = Pb + uint32_t(slot) * GS_PBYTES + uint32_t(phalf * 8 * 16 + prow) * 8u;
+#pragma unroll
+      for (int st = 0; st < 8; ++st) {
+        const float c1 = p.with_scaling ? gs_raw_to_float<T>(sp[st]) : 1.f;
+        float c2;
+        if (p.zmode == 0) c2 = -c1 * float(p.zp_const);
+        else if (p.zmode == 1) c2 = -c1 * gs_raw_to_float<T>(zp[st]);
+        else if (p.zmode == 2) c2 = -gs_raw_to_float<T>(zp[st]);
+        else c2 = -c1 * float((zp[st] >> (4 * (prow & 1))) & 15u);
+        gs_sts64f(pbase + uint32_t(st) * 128u, c1, c2);
+      }
+      __syncwarp();
+      if (lane == 0) gs_mbar_arrive(Bb + 8u * slot);
+      if (++slot == S) { slot = 0; ephase ^= 1u; }
+    };
+    if (n_units > 0) fetch(sA, zA);
+#pragma unroll 1
+    for (int i = 0; i < n_units; i += 2) {
+      if (i + 1 < n_units) fetch(sB, zB);
+      convert(sA, zA);
+      if (i + 1 < n_units) {
+        if (i + 2 < n_units) fetch(sA, zA);
+        convert(sB, zB);
+      }
+    }
+    return;
+  }
+
+  // =========================== consumer warps ===========================
+  const int w = warp;
+  const int r = lane >> 2, q = lane & 3;
+  // MMA fragment row r <-> weight row rr of the block (rows r+8 <-> rr+8): the two rows met by one ld.shared phase
+  // (lanes 8i..8i+7: r = 2i, 2i+1) are rr = i and i+4, 4 * 16 B = 64 B apart in bank space (GS_ROW_PITCH) -> conflict-free
+  const int rr = (r >> 1) | ((r & 1) << 2);
+  const uint32_t woff_a = uint32_t(rr) * GS_ROW_PITCH + uint32_t(w) * GS_SLICE_BYTES + uint32_t(q) * 16u;
+  const uint32_t woff_b = woff_a + 8u * GS_ROW_PITCH;
+  constexpr uint32_t ch0 = 0u, ch1 = 64u;   // the lane's two 16-byte chunks of its rows' 128-byte slice (k steps 2w, 2w+1)
+  const uint32_t aoff = uint32_t(w) * 512u + uint32_t(q) * 64u;
+  const uint32_t poff = uint32_t(2 * w * 16 + rr) * 8u;
+  const uint32_t soff = uint32_t(2 * w) * 8u;
+
+  uint32_t Rv[2][4][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) Rv[j][x][y] = 0u;
+
+  float acc_a = 0.f, acc_b = 0.f;   // rows rr and rr+8, column 0 (meaningful in lanes q == 0)
+  int slot = 0, rbuf = 0;
+  uint32_t fphase = 0u;
+  int rb = t0 / UPR, ku = t0 - rb * UPR;
+  bool seg_from0 = (ku == 0);
+  const int nsl_last = (Kb - (UPR - 1) * (GS_NCONS * GS_SLICE_BYTES)) / GS_SLICE_BYTES;   // valid K-slices of a row block's last unit
+  uint32_t wst = Wb, ast = Ab + aoff, pst = Pb + poff;
+  uint32_t fbar = Bb, ebar = Bb + 8u * uint32_t(S);
+
+#pragma unroll 1
+  for (int t = t0; t < t1; ++t) {
+    const bool closes = (ku == UPR - 1);
+    gs_mbar_wait(fbar, fphase);
+    if (!closes || w < nsl_last) {
+      const uint32_t sst = SUMb + soff + uint32_t(ku) * (GS_STEPS * 8u);
+      uint4 wv[2][2];
+      wv[0][0] = gs_lds128(wst + woff_a + ch0);
+      wv[0][1] = gs_lds128(wst + woff_b + ch0);
+      wv[1][0] = gs_lds128(wst + woff_a + ch1);
+      wv[1][1] = gs_lds128(wst + woff_b + ch1);
+      if (r == 0) {   // m = 1: only MMA column 0 (lanes 0..3) carries activations; one divergent region per stage
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const uint4 v = gs_lds128(ast + uint32_t(j * 256 + x * 16));
+            Rv[j][x][0] = v.x; Rv[j][x][1] = v.y; Rv[j][x][2] = v.z; Rv[j][x][3] = v.w;
+          }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 pa = gs_lds64f(pst + uint32_t(j) * 128u);
+        const float2 pb = gs_lds64f(pst + uint32_t(j) * 128u + 64u);
+        const float2 su = gs_lds64f(sst + uint32_t(j) * 8u);
+        const uint32_t wa[4] = {wv[j][0].x, wv[j][0].y, wv[j][0].z, wv[j][0].w};
+        const uint32_t wb[4] = {wv[j][1].x, wv[j][1].y, wv[j][1].z, wv[j][1].w};
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+          uint32_t ha[4], hb[4];
+          if constexpr (HI) {
+            const uint32_t xa = wa[wi], ya = wa[wi] >> 8, xb = wb[wi], yb = wb[wi] >> 8;
+            ha[0] = lop3_and_or(xa, 0x000f000fu, MAGIC); ha[1] = lop3_and_or(xa, 0x00f000f0u, MAGIC_HI);
+            ha[2] = lop3_and_or(ya, 0x000f000fu, MAGIC); ha[3] = lop3_and_or(ya, 0x00f000f0u, MAGIC_HI);
+            hb[0] = lop3_and_or(xb, 0x000f000fu, MAGIC); hb[1] = lop3_and_or(xb, 0x00f000f0u, MAGIC_HI);
+            hb[2] = lop3_and_or(yb, 0x000f000fu, MAGIC); hb[3] = lop3_and_or(yb, 0x00f000f0u, MAGIC_HI);
+          } else {
+            decode_u4x8_raw<T>(wa[wi], ha);
+            decode_u4x8_raw<T>(wb[wi], hb);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const uint32_t af[4] = {ha[2 * jj], hb[2 * jj], ha[2 * jj + 1], hb[2 * jj + 1]};
+            uint32_t b0, b1;
+            if constexpr (IL) {
+              b0 = Rv[j][wi][2 * jj]; b1 = Rv[j][wi][2 * jj + 1];
+            } else {
+              b0 = __byte_perm(Rv[j][wi][jj], Rv[j][wi][jj + 2], 0x5410);
+              b1 = __byte_perm(Rv[j][wi][jj], Rv[j][wi][jj + 2], 0x7632);
+            }
+            gs_mma<T>(c, af, b0, b1);
+          }
+        }
+        acc_a = fmaf(pa.x, c[0] - su.x, acc_a);
+        acc_a = fmaf(pa.y, su.y, acc_a);
+        acc_b = fmaf(pb.x, c[2] - su.x, acc_b);
+        acc_b = fmaf(pb.y, su.y, acc_b);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) gs_mbar_arrive(ebar);
+    wst += GS_WBYTES; ast += GS_ABYTES; pst += GS_PBYTES; fbar += 8u; ebar += 8u;
+    if (++slot == S) {
+      slot = 0; fphase ^= 1u;
+      wst = Wb; ast = Ab + aoff; pst = Pb + poff; fbar = Bb; ebar = Bb + 8u * uint32_t(S);
+    }
+
+    if (closes || t == t1 - 1) {
+      // ---- end of this range's segment of row block rb: CTA reduction over the 8 K-slices, then store / park / collect ----
+      const uint32_t rbase = Rb + uint32_t(rbuf) * (GS_NCONS * 16 * 4);
+      if (q == 0) {
+        gs_sts32f(rbase + uint32_t(w * 16 + rr) * 4u, acc_a);
+        gs_sts32f(rbase + uint32_t(w * 16 + rr + 8) * 4u, acc_b);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(GS_NCONS * 32) : "memory");
+      if (threadIdx.x < 16) {
+        const int row = threadIdx.x;
+        float v = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < GS_NCONS; ++ww) v += gs_lds32f(rbase + uint32_t(ww * 16 + row) * 4u);
+        if (!seg_from0) {
+          // contribution to a row block owned by a later range (only the first segment of a range can be one)
+          const unsigned long long pk = (static_cast<unsigned long long>(p.nonce) << 32) | __float_as_uint(v);
+          asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.ws + size_t(ri) * 16 + row), "l"(pk) : "memory");
+        } else {
+          if (!closes) {
+            // this range owns the block but does not reach its end: add the parked sums of the ranges that cover the rest
+            const int rb_end = (rb + 1) * UPR;
+            for (int rj = ri + 1; rj < R; ++rj) {
+              const int b = gs_range_begin(rj, p.T, R), e = gs_range_begin(rj + 1, p.T, R);
+              if (b >= rb_end) break;
+              if (b == e) continue;
+              unsigned long long* sl = p.ws + size_t(rj) * 16 + row;
+              unsigned long long pk;
+              do {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(pk) : "l"(sl) : "memory");
+              } while (static_cast<unsigned int>(pk >> 32) != p.nonce);
+              v += __uint_as_float(static_cast<unsigned int>(pk));
+              asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(sl), "l"(0ull) : "memory");
+              if (e >= rb_end) break;
+            }
+          }
+          gs_store<T>(p, rb * 16 + row, v);
+        }
+      }
+      acc_a = acc_b = 0.f;
+      rbuf ^= 1;
+      seg_from0 = true;
+    }
+    if (++ku == UPR) { ku = 0; ++rb; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int gs_smem_bytes(int stages, int K) { return 1024 + stages * GS_STAGE_BYTES + GS_RED_BYTES + 16 * GS_MAX_STAGES + (K / 128) * 8 + 64; }
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+constexpr int GS_MAX_DEVICES = BB_MAX_DEVICES;
+
+template <typename KernelT>
+int gs_occupancy(KernelT k, int variant, int smem, int dev) {
+  // per (kernel variant, device): opt-in shared memory once (the device maximum); per dynamic size: occupancy, cached
+  struct Entry { int smem, occ; };
+  static std::mutex mu;
+  static Entry cache[16][GS_MAX_DEVICES][8];
+  static int used[16][GS_MAX_DEVICES];
+  static bool attr[16][GS_MAX_DEVICES];
+  static bool init = false;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!init) { memset(cache, 0, sizeof(cache)); memset(used, 0, sizeof(used)); memset(attr, 0, sizeof(attr)); init = true; }
+  if (!attr[variant][dev]) {
+    int optin = 0;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) { cudaGetLastError(); return -1; }
+    attr[variant][dev] = true;
+  }
+  Entry* e = cache[variant][dev];
+  int& n = used[variant][dev];
+  for (int i = 0; i < n; ++i) if (e[i].smem == smem) return e[i].occ;
+  int o = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, GS_THREADS, size_t(smem)) != cudaSuccess) { cudaGetLastError(); o = 0; }
+  const int occ = o < 1 ? -1 : o;
+  const int slot = n < 8 ? n++ : 7;
+  e[slot] = Entry{smem, occ};
+  return occ;
+}
+
+}  // namespace
+
+size_t gemv_slab_workspace_bytes() { return size_t(GS_MAX_CPS) * size_t(device_sm_count()) * 16 * 8 + 256; }
+
+bool gemv_slab_supported(const bb_matmul_desc& d, int m) {
+  if (m != 1) return false;
+  if (d.a_dtype != BB_F16 && d.a_dtype != BB_BF16) return false;
+  if (d.w_fmt != BB_W_UINT && d.w_fmt != BB_W_INT) return false;
+  if (d.w_bits != 4) return false;
+  if (d.w_layout == BB_LAYOUT_INTERLEAVED_8) return false;
+  if (d.N % 16 || d.K % 256) return false;
+  const int g = d.group_size <= 0 ? d.K : d.group_size;
+  if (g % 128 || d.K % g) return false;
+  if (d.with_zeros && !d.with_scaling) return false;
+  if (d.w_fmt == BB_W_INT && d.with_zeros) return false;
+  if (d.out_dtype != BB_F16 && d.out_dtype != BB_BF16 && d.out_dtype != BB_F32) return false;
+  if (d.with_zeros && d.zeros_mode == BB_ZEROS_QUANTIZED && (d.N % 2)) return false;
+  if ((long long)(d.N / 16) * ((d.K + GS_KU - 1) / GS_KU) >= (1ll << 30)) return false;
+  return true;
+}
+
+int launch_gemv_slab(const MatmulArgs& a) {
+  const bb_matmul_desc& d = a.d;
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15)) {
+    set_error("gemv_slab: A and W must be 16-byte aligned (bulk copies)");
+    return 5;
+  }
+  if (!a.workspace || a.workspace_bytes < gemv_slab_workspace_bytes()) {
+    set_error("gemv_slab needs a zero-initialised workspace of %zu bytes (bb_workspace_bytes)", gemv_slab_workspace_bytes());
+    return 5;
+  }
+  const int dev = current_device();
+  SlabParams p;
+  p.A = a.A; p.scale = d.with_scaling ? a.scale : nullptr; p.zeros = d.with_zeros ? a.zeros : nullptr;
+  p.bias = d.with_bias ? a.bias : nullptr; p.out = make_outspec(a);
+  p.N = d.N; p.K = d.K; p.G = a.groups(); p.g128 = a.gsize() / 128;
+  p.with_scaling = d.with_scaling;
+  p.zmode = d.with_zeros ? (d.zeros_mode + 1) : 0;
+  p.zp_const = (d.w_fmt == BB_W_INT) ? (1 << (d.w_bits - 1)) : 0;
+  p.out_dtype = d.out_dtype;
+  p.UPR = (d.K + GS_KU - 1) / GS_KU;
+  p.T = (d.N / 16) * p.UPR;
+  int stages = env_int("BB_GS_STAGES", 4);
+  stages = std::max(2, std::min(GS_MAX_STAGES, stages));
+  p.stages = stages;
+  p.W = reinterpret_cast<const uint8_t*>(a.W);
+  p.vec_scale = (d.with_scaling && p.g128 == 1 && (p.G & 7) == 0 && (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0) ? 1 : 0;
+  p.ws = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(a.workspace) + 15) & ~uintptr_t(15));
+  static std::atomic<unsigned int> counter{0x9e3779b9u};
+  unsigned int nz = counter.fetch_add(0x9e3779b9u);
+  p.nonce = nz | 1u;
+  int cps = env_int("BB_GS_CPS", 2);
+  cps = std::max(1, std::min(GS_MAX_CPS, cps));
+  const bool il = d.w_layout == BB_LAYOUT_INTERLEAVED_16;
+  const bool f16 = d.a_dtype == BB_F16;
+  const int smem = gs_smem_bytes(stages, d.K);
+  const int sms = device_sm_count();
+  static const bool pdl = [] { const char* e = getenv("BB_PDL"); return e ? atoi(e) != 0 : true; }();
+
+#define BB_GS_GO(TT, ILV, CPSV, VAR)                                                                   \
+  {                                                                                                    \
+    auto k = gemv_slab_kernel<TT, ILV, CPSV>;                                                          \
+    int occ = gs_occupancy(k, VAR, smem, dev);                                                       \
+    if (occ < 0) { set_error("gemv_slab: kernel does not fit on this device (stages=%d, K=%d)", stages, d.K); return 4; } \
+    occ = std::min(occ, CPSV);                                                                         \
+    const int grid = std::max(1, std::min(p.T, occ * sms));                                            \
+    cudaLaunchConfig_t cfg = {};                                                                       \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GS_THREADS);                                         \
+    cfg.dynamicSmemBytes = smem; cfg.stream = a.stream;                                                \
+    cudaLaunchAttribute attr[1];                                                                       \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                   \
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;                                  \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                                                \
+    BB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, p));                                                 \
+  }
+#define BB_GS_CPS(TT, ILV, VB)                                  \
+  if (cps == 1) BB_GS_GO(TT, ILV, 1, VB + 0)                    \
+  else if (cps == 2) BB_GS_GO(TT, ILV, 2, VB + 1)               \
+  else BB_GS_GO(TT, ILV, 3, VB + 2)
+  if (f16) { if (il) { BB_GS_CPS(__half, true, 0) } else { BB_GS_CPS(__half, false, 3) } }
+  else { if (il) { BB_GS_CPS(__nv_bfloat16, true, 6) } else { BB_GS_CPS(__nv_bfloat16, false, 9) } }
+#undef BB_GS_CPS
+#undef BB_GS_GO
+  BB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace bb

@@ -107,6 +107,39 @@ __global__ void debug_decode16_kernel(int bits, int zp, int layout, const uint32
   }
 }
 
+// the GEMM path's dequant arithmetic (dq_finish) over an array of packed words; one (scale, zeros, qzeros) triple per group of 8
+// outputs, like the reference's decode_*_scale[_zeros_*] device functions (fast_decoding.hpp) which the KATs compare against
+template <typename T, int MODE>
+__global__ void debug_dequant16_kernel(int bits, int zp, int layout, const uint32_t* __restrict__ in, const T* __restrict__ scale,
+                                       const T* __restrict__ zeros, const int* __restrict__ qzeros, T* __restrict__ out, int nwords) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nwords) return;
+  const uint32_t w = in[i];
+  const int per_word = 32 / bits, gpw = per_word / 8;   // outputs and 8-output groups per 32-bit word
+  uint32_t h[8];
+  if (bits == 4) { uint32_t t[4]; decode_u4x8_raw<T>(w, t); for (int j = 0; j < 4; ++j) h[j] = t[j]; }
+  else if (layout == BB_LAYOUT_COMPRESSED) decode_u2x16_raw_compressed<T>(w, h);
+  else decode_u2x16_raw_interleaved<T>(w, h);
+  for (int j = 0; j < per_word / 2; ++j) {
+    const int i0 = layout == BB_LAYOUT_COMPRESSED ? j : 2 * j, i1 = layout == BB_LAYOUT_COMPRESSED ? j + per_word / 2 : 2 * j + 1;
+    uint16_t r[2];
+    const int idx[2] = {i0, i1};
+    for (int e = 0; e < 2; ++e) {   // the two halves of a pair may belong to different 8-output groups (compressed layout)
+      const int g = i * gpw + idx[e] / 8;
+      DqConst c;
+      const uint32_t zq = (MODE == 4) ? uint32_t(qzeros[g]) : 0u;
+      c.mz_lo = c.mz_hi = TypeTraits<T>::kMagic + (uint32_t(zp) + zq) * 0x00010001u;
+      c.s2 = MODE != 0 ? dup2<T>(scale[g]) : 0u;
+      c.z2 = (MODE == 2 || MODE == 3) ? dup2<T>(zeros[g]) : 0u;
+      c.negz2 = c.z2 ^ 0x80008000u;
+      const uint32_t v = dq_finish<T, MODE>(h[j], c.mz_lo, c);
+      r[e] = e == 0 ? uint16_t(v & 0xffff) : uint16_t(v >> 16);
+    }
+    out[size_t(per_word) * i + i0] = *reinterpret_cast<const T*>(&r[0]);
+    out[size_t(per_word) * i + i1] = *reinterpret_cast<const T*>(&r[1]);
+  }
+}
+
 __global__ void debug_decode8_kernel(int bits, int zp, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int nwords) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nwords) return;
@@ -222,6 +255,28 @@ int bb_debug_decode(int kind, int bits, int is_signed, int w_layout, const void*
     if (w_layout != BB_LAYOUT_INTERLEAVED_8) { set_error("int8 decode needs the interleaved-8 layout"); return 1; }
     debug_decode8_kernel<<<blocks, threads, 0, s>>>(bits, zp, (const uint32_t*)in, (uint32_t*)out, nwords);
   } else { set_error("bb_debug_decode: bad kind"); return 1; }
+  BB_LAUNCH_CHECK();
+  return 0;
+}
+
+int bb_debug_dequant(int kind, int bits, int is_signed, int w_layout, int mode, const void* in, const void* scale,
+                     const void* zeros, const void* qzeros, void* out, int nwords, void* stream) {
+  if ((bits != 2 && bits != 4) || !in || !out || mode < 0 || mode > 4 || (kind != 0 && kind != 1)) { set_error("bb_debug_dequant: bad arguments"); return 1; }
+  if (w_layout != BB_LAYOUT_COMPRESSED && w_layout != BB_LAYOUT_INTERLEAVED_16) { set_error("bb_debug_dequant: 16-bit layouts only"); return 1; }
+  if ((mode >= 1 && !scale) || ((mode == 2 || mode == 3) && !zeros) || (mode == 4 && !qzeros)) { set_error("bb_debug_dequant: missing operand"); return 1; }
+  const int zp = is_signed ? (1 << (bits - 1)) : 0;
+  const int threads = 128, blocks = (nwords + threads - 1) / threads;
+  cudaStream_t s = (cudaStream_t)stream;
+#define BB_DQ_GO(TT)                                                                                                              \
+  switch (mode) {                                                                                                                 \
+    case 0: debug_dequant16_kernel<TT, 0><<<blocks, threads, 0, s>>>(bits, zp, w_layout, (const uint32_t*)in, (const TT*)scale, (const TT*)zeros, (const int*)qzeros, (TT*)out, nwords); break; \
+    case 1: debug_dequant16_kernel<TT, 1><<<blocks, threads, 0, s>>>(bits, zp, w_layout, (const uint32_t*)in, (const TT*)scale, (const TT*)zeros, (const int*)qzeros, (TT*)out, nwords); break; \
+    case 2: debug_dequant16_kernel<TT, 2><<<blocks, threads, 0, s>>>(bits, zp, w_layout, (const uint32_t*)in, (const TT*)scale, (const TT*)zeros, (const int*)qzeros, (TT*)out, nwords); break; \
+    case 3: debug_dequant16_kernel<TT, 3><<<blocks, threads, 0, s>>>(bits, zp, w_layout, (const uint32_t*)in, (const TT*)scale, (const TT*)zeros, (const int*)qzeros, (TT*)out, nwords); break; \
+    default: debug_dequant16_kernel<TT, 4><<<blocks, threads, 0, s>>>(bits, zp, w_layout, (const uint32_t*)in, (const TT*)scale, (const TT*)zeros, (const int*)qzeros, (TT*)out, nwords); break; \
+  }
+  if (kind == 0) { BB_DQ_GO(__half) } else { BB_DQ_GO(__nv_bfloat16) }
+#undef BB_DQ_GO
   BB_LAUNCH_CHECK();
   return 0;
 }

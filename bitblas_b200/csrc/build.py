@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["bb_api.cu", "bb_generic.cu", "bb_gemv.cu", "bb_gemm_ts.cu", "bb_prep.cu"]
+SOURCES = ["bb_api.cu", "bb_generic.cu", "bb_gemv.cu", "bb_gemv_slab.cu", "bb_gemm_ts.cu", "bb_prep.cu"]
 HEADERS = ["bb_common.cuh", os.path.join(PKG, "..", "include", "bitblas_b200.h")]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("BB_PTXAS_V") else "-O3"]

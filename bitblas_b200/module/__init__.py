@@ -56,9 +56,14 @@ def unpack_qweight(qweight, bits):
 
 
 class Linear(nn.Module):
+    """Drop-in for ``bitblas.Linear``.  Public surface kept from the reference (module/__init__.py:77-370): constructor
+    signature, the registered buffers and their shapes (so reference state dicts load), ``bitblas_matmul``, ``bits``,
+    ``source_format``, ``opt_M``, ``q_params`` / ``init_params()``, ``consistent``, ``forward``, ``warmup``,
+    ``load_and_transform_weight``, ``repack_from_gptq[_v2]``.  Everything underneath is this package's own."""
+
     opt_M = [16, 32, 64, 128, 256, 512]
     STORAGE_DTYPE = "int8"
-    TORCH_STORAGE_DTYPE = getattr(torch, STORAGE_DTYPE)
+    TORCH_STORAGE_DTYPE = torch.int8
     BITBLAS_DTYPES = {torch.float32: "float32", torch.float16: "float16", torch.half: "float16", torch.int8: "int8"}
 
     def __init__(self, in_features: int, out_features: int, bias: bool = False, A_dtype: str = "float16",
@@ -67,84 +72,52 @@ class Linear(nn.Module):
                  opt_M: Union[int, List[int]] = opt_M, enable_tuning: bool = True,
                  fast_decoding: Optional[bool] = None, propagate_b: bool = False):
         super().__init__()
-        self.in_features = in_features
-        self.out_features = out_features
-        self.opt_M = opt_M
-        self.group_size = self._set_group_size(group_size, in_features)
-        self.torch_dtype = getattr(torch, A_dtype)
-        self.is_consitent = A_dtype == W_dtype
-        self.zeros_mode = zeros_mode
-        self._validate_parameters(self.group_size, in_features, out_features)
-        self._configure_bitblas_matmul(A_dtype, W_dtype, accum_dtype, out_dtype, with_scaling, with_zeros, zeros_mode,
-                                       enable_tuning, fast_decoding, bias, propagate_b)
-        self._initialize_buffers(in_features, out_features, bias)
-        self.q_params = None
-
-    def _param_ptrs(self):
-        cfg = self.bitblas_matmul.config
-        ptrs = [self.qweight.data_ptr()]
-        if cfg.with_scaling:
-            ptrs.append(self.scales.data_ptr())
-        if cfg.with_zeros:
-            ptrs.append(self.zeros.data_ptr())
-        if cfg.with_bias:
-            ptrs.append(self.bias.data_ptr())
-        return tuple(ptrs)
-
-    def init_params(self):
-        if self.is_consitent:
-            param_list = [self.weight]
-            if self.bitblas_matmul.config.with_bias:
-                param_list.append(self.bias)
-        else:
-            param_list = [self.qweight]
-            if self.bitblas_matmul.config.with_scaling:
-                param_list.append(self.scales)
-            if self.bitblas_matmul.config.with_zeros:
-                param_list.append(self.zeros)
-            if self.bitblas_matmul.config.with_bias:
-                param_list.append(self.bias)
-        self.q_params = [ctypes.c_void_p(arr.data_ptr()) for arr in param_list]
-        self._q_param_key = tuple(arr.data_ptr() for arr in param_list)
-
-    def _validate_parameters(self, group_size, in_features, out_features):
-        if in_features % 16 != 0 or out_features % 16 != 0:
+        if in_features % 16 or out_features % 16:
             raise ValueError("`in_features` and `out_features` must be divisible by 16.")
-        if in_features % group_size != 0:
+        gsize = in_features if group_size in (-1, None) else int(group_size)
+        if gsize <= 0 or in_features % gsize:
             raise ValueError("`in_features` must be divisible by `group_size`.")
-
-    def _set_group_size(self, group_size, in_features):
-        return in_features if (group_size == -1 or group_size is None) else group_size
-
-    def _initialize_buffers(self, in_features, out_features, bias):
-        if self.consistent:
-            self.register_buffer("weight", torch.zeros((out_features, in_features // self.group_size), dtype=self.torch_dtype))
-        else:
-            self.register_buffer("qweight", torch.zeros(self.bitblas_matmul.retrieve_weight_shape(), dtype=self.TORCH_STORAGE_DTYPE))
-            self.register_buffer("scales", torch.zeros((out_features, in_features // self.group_size), dtype=self.torch_dtype))
-            if self.zeros_mode == "quantized":
-                storage_nbit = int("".join(c for c in self.STORAGE_DTYPE if c.isdigit()))
-                self.register_buffer("zeros", torch.zeros((in_features // self.group_size, out_features // storage_nbit * self.bits),
-                                                          dtype=self.TORCH_STORAGE_DTYPE))
-            else:
-                self.register_buffer("zeros", torch.zeros((out_features, in_features // self.group_size), dtype=self.torch_dtype))
-        if bias:
-            self.register_buffer("bias", torch.zeros((out_features), dtype=self.torch_dtype))
-        else:
-            self.bias = None
-
-    def _configure_bitblas_matmul(self, A_dtype, W_dtype, accum_dtype, out_dtype, with_scaling, with_zeros, zeros_mode,
-                                  enable_tuning, fast_decoding, bias, propagate_b):
-        matmul_config = MatmulConfig(M=self.opt_M, N=self.out_features, K=self.in_features, A_dtype=A_dtype,
-                                     W_dtype=W_dtype, accum_dtype=accum_dtype, out_dtype=out_dtype,
-                                     storage_dtype=self.STORAGE_DTYPE, with_scaling=with_scaling, with_zeros=with_zeros,
-                                     group_size=self.group_size, fast_decoding=fast_decoding, with_bias=bias,
-                                     propagate_b=propagate_b, zeros_mode=zeros_mode)
-        self.bitblas_matmul = self._get_or_create_bitblas_operator(matmul_config, enable_tuning)
+        self.in_features, self.out_features = in_features, out_features
+        self.opt_M = opt_M
+        self.group_size = gsize
+        self.zeros_mode = zeros_mode
+        self.torch_dtype = getattr(torch, A_dtype)
+        self.is_consitent = A_dtype == W_dtype   # (sic) attribute name read by integrations of the reference
+        config = MatmulConfig(M=opt_M, N=out_features, K=in_features, A_dtype=A_dtype, W_dtype=W_dtype,
+                              accum_dtype=accum_dtype, out_dtype=out_dtype, storage_dtype=self.STORAGE_DTYPE,
+                              group_size=gsize, with_scaling=with_scaling, with_zeros=with_zeros, zeros_mode=zeros_mode,
+                              with_bias=bias, fast_decoding=fast_decoding, propagate_b=propagate_b)
+        self.bitblas_matmul = self._operator_for(config)
         self.bits = self.bitblas_matmul.bit
         self.source_format = self.bitblas_matmul.source_format
+        for name, shape, dtype in self._buffer_specs(bias):
+            self.register_buffer(name, torch.zeros(shape, dtype=dtype))
+        if not bias:
+            self.bias = None
+        self.q_params = None
+        self._q_param_key = None
 
-    def _get_or_create_bitblas_operator(self, config, enable_tuning):
+    # ---- construction helpers ------------------------------------------------------------------------
+    def _buffer_specs(self, bias: bool):
+        """(name, shape, dtype) of every registered buffer; shapes follow module/__init__.py:164-205."""
+        n, groups = self.out_features, self.in_features // self.group_size
+        specs = []
+        if self.consistent:
+            specs.append(("weight", (n, self.in_features), self.torch_dtype))
+        else:
+            specs.append(("qweight", tuple(self.bitblas_matmul.retrieve_weight_shape()), self.TORCH_STORAGE_DTYPE))
+            specs.append(("scales", (n, groups), self.torch_dtype))
+            if self.zeros_mode == "quantized":
+                specs.append(("zeros", (groups, n * self.bits // 8), self.TORCH_STORAGE_DTYPE))   # `bits`-packed along N
+            else:
+                specs.append(("zeros", (n, groups), self.torch_dtype))
+        if bias:
+            specs.append(("bias", (n,), self.torch_dtype))
+        return specs
+
+    @staticmethod
+    def _operator_for(config: MatmulConfig) -> Matmul:
+        """one Matmul per distinct config, shared through the process-wide cache like the reference (:245-256)."""
         target = auto_detect_nvidia_target()
         if global_operator_cache.size() == 0:
             global_operator_cache.load_from_database(BITBLAS_DATABASE_PATH, target)
@@ -152,10 +125,21 @@ class Linear(nn.Module):
         if op is None:
             op = Matmul(config, target=target, enable_tuning=False)
             global_operator_cache.add(config, op)
-            logger.info("BitBLAS Operator created.")
-        else:
-            logger.info("BitBLAS Operator found in global_operator_cache.")
         return op
+
+    def _live_params(self):
+        """tensors `lib.call` needs after the activations, in the reference's positional order."""
+        cfg = self.bitblas_matmul.config
+        if self.consistent:
+            named = [("weight", True), ("bias", cfg.with_bias)]
+        else:
+            named = [("qweight", True), ("scales", cfg.with_scaling), ("zeros", cfg.with_zeros), ("bias", cfg.with_bias)]
+        return [getattr(self, name) for name, used in named if used]
+
+    def init_params(self):
+        tensors = self._live_params()
+        self.q_params = [ctypes.c_void_p(t.data_ptr()) for t in tensors]
+        self._q_param_key = tuple(t.data_ptr() for t in tensors)
 
     def warmup(self, topk=20):
         self.bitblas_matmul.hardware_aware_finetune(topk=topk)
@@ -174,7 +158,7 @@ class Linear(nn.Module):
             raise ValueError(f"A has inner dimension {A.shape[-1]}, expected {self.in_features}")
         stream = torch.cuda.current_stream(A.device)
         # the reference rebuilds this list on every call (module/__init__.py:274); rebuild only if a buffer moved
-        if self.q_params is None or self._q_param_key != self._param_ptrs():
+        if self.q_params is None or self._q_param_key != tuple(t.data_ptr() for t in self._live_params()):
             self.init_params()
         if output is None:
             output = torch.empty(A.shape[:-1] + (self.out_features,), dtype=getattr(torch, op.out_dtype), device=A.device)

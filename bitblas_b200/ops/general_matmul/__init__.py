@@ -193,6 +193,10 @@ class _LibShim:
         m = int(args.pop()) if op.dynamic_range is not None else int(op.M)
         ptrs = [self._ptr(a) for a in args]
         expect = 3 + int(op.lut is not None) + int(op.with_scaling) + int(op.with_zeros) + int(op.with_bias)
+        if op.lut is not None and len(ptrs) == expect - 1:
+            # bitblas.Linear-style callers pass A, qweight, [scales], [zeros], [bias], C and never the NF4 table
+            # (module/__init__.py:275-287 has the same omission): supply the operator's own
+            ptrs.insert(2, op.lut.data_ptr())
         if len(ptrs) != expect:
             raise TypeError(f"lib.call expected {expect} buffers (A, W, [lut], [scale], [zeros], [bias], C), got {len(ptrs)}")
         it = iter(ptrs)
@@ -250,6 +254,7 @@ class Matmul(Operator):
                 self.lut = self.lut.cuda()
         self._desc = None
         self._ws = {}
+        self._ws_need = {}
         self.weight_executors = None
         self.input_executors = None
         if not self.consistent:
@@ -392,16 +397,20 @@ class Matmul(Operator):
         return output
 
     def _workspace_for(self, m: int, device):
-        """scratch for split-K partials (bb_workspace_bytes); one cached buffer per operator and device, grown on demand.
-        Stream-ordered reuse: the reduce kernel of call i reads it before the matmul of call i+1 (same stream) writes it."""
-        # (the size depends on the kernel the dispatcher would pick, which a test may have pinned: not cached across overrides)
-        need = int(self.lib._c.bb_workspace_bytes(ctypes.byref(self._desc), int(m)))
+        """scratch the kernel picked for `m` needs (bb_workspace_bytes: split-K partials, stream-K exchange slots); one cached,
+        ZERO-INITIALISED buffer per operator, device and stream, grown on demand.  The stream-K kernels leave their slots
+        zero-tagged, so the buffer is reused by later calls on the same stream without clearing (include/bitblas_b200.h)."""
+        key = (int(m), _lib.OVERRIDE_GEN)
+        need = self._ws_need.get(key)
+        if need is None:
+            need = self._ws_need[key] = int(self.lib._c.bb_workspace_bytes(ctypes.byref(self._desc), int(m)))
         if need == 0:
             return 0, 0
-        ws = self._ws.get(device)
+        wkey = (device, torch.cuda.current_stream(device).cuda_stream)
+        ws = self._ws.get(wkey)
         if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=device)
-            self._ws[device] = ws
+            ws = torch.zeros(need, dtype=torch.uint8, device=device)
+            self._ws[wkey] = ws
         return ws.data_ptr(), ws.numel()
 
     def forward_scatter(self, A, W, scale=None, zeros=None, bias=None, *, peer_ptrs, ldc: int, col_offset: int):
@@ -437,20 +446,49 @@ class Matmul(Operator):
             raise RuntimeError(f"bb_matmul_scatter failed (code {rc}): {_lib.last_error()}")
 
     def _forward_consistent(self, A, W, bias, output):
-        # A_dtype == W_dtype (no sub-byte decode): outside the hot path; library GEMM.
-        if not A.is_cuda:
-            raise RuntimeError("A must be a CUDA tensor: bitblas_b200 has no CPU path")
-        if self.A_dtype == "int8":
-            out = torch.matmul(A.reshape(-1, A.shape[-1]).to(torch.int32).float(), W.to(torch.int32).float().t())
-            out = out.to(self.torch_output_dtype).reshape(A.shape[:-1] + (self.N,))
+        """A_dtype == W_dtype (no sub-byte decode; general_matmul/__init__.py:33-51,568-580): a plain library GEMM, outside the
+        hot path.  float16 / bfloat16: cuBLAS through torch.matmul (fp32 accumulate).  int8: EXACT int32
+        accumulation through cuBLASLt (torch._int_mm), like the reference's INT8xINT8 kernels -- never through fp32, whose
+        partial sums stop being exact at 2^24.  float8: operands widened to float16 (exact), fp32 accumulate."""
+        if not A.is_cuda or not W.is_cuda:
+            raise RuntimeError("A and W must be CUDA tensors: bitblas_b200 has no CPU path")
+        c = self.config
+        if W.shape[-1] != c.K or W.shape[0] != c.N or A.shape[-1] != c.K:
+            raise ValueError(f"expected A[..., {c.K}] and W[{c.N}, {c.K}], got {tuple(A.shape)} and {tuple(W.shape)}")
+        a2 = A.reshape(-1, c.K)
+        if c.A_dtype in ("int8", "uint8"):
+            if a2.dtype != torch.int8 or W.dtype != torch.int8:
+                raise TypeError("the int8 dense path takes int8 A and W")
+            acc = self._int8_gemm_exact(a2.contiguous(), W.contiguous())
+            if bias is not None:
+                acc = acc + bias.to(torch.int32)
+            out = acc.to(self.torch_output_dtype)
         else:
-            out = torch.matmul(A, W.t()).to(self.torch_output_dtype)
-        if bias is not None:
-            out = out + bias.to(out.dtype)
+            if c.A_dtype in ("e4m3_float8", "e5m2_float8"):
+                a2, W = a2.to(torch.float16), W.to(torch.float16)
+            out = torch.matmul(a2, W.t()).to(self.torch_output_dtype)
+            if bias is not None:
+                out = out + bias.to(out.dtype)
+        out = out.reshape(A.shape[:-1] + (c.N,))
         if output is not None:
             output.copy_(out)
             return output
         return out
+
+    @staticmethod
+    def _int8_gemm_exact(a2: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+        """int32 = int8 [m, K] x int8 [N, K]^T.  torch._int_mm needs m > 16 and K, N multiples of 8: rows are zero-padded,
+        other shapes take the (exact, slower) float64 GEMM."""
+        m, K = a2.shape
+        N = W.shape[0]
+        if K % 8 == 0 and N % 8 == 0:
+            rows = max(32, (m + 7) // 8 * 8)
+            if rows != m:
+                pad = torch.zeros((rows, K), dtype=torch.int8, device=a2.device)
+                pad[:m] = a2
+                a2 = pad
+            return torch._int_mm(a2, W.t())[:m]
+        return torch.matmul(a2.double(), W.double().t()).to(torch.int32)
 
     def __call__(self, *args: Any, **kwds: Any) -> Any:
         return self.forward(*args, **kwds)

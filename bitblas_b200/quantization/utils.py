@@ -12,29 +12,19 @@ import torch.nn as nn
 
 
 def gen_quant4(k, n, groupsize=-1):
-    """Test helper of the reference (quantization/utils.py:8-51): random fp16 weight -> symmetric 4-bit."""
-    maxq = 2**4
-    w = torch.randn((k, n), dtype=torch.half, device="cpu")
-    original_w = w.clone()
-    if groupsize == -1:
-        groupsize = k
-    w = w.reshape((-1, groupsize, n)).permute(1, 0, 2).reshape((groupsize, -1))
-    s = torch.max(torch.abs(w), 0, keepdim=True)[0]
-    s *= 2 / maxq
-    w = torch.round(w / s).int()
-    w += maxq // 2
-    w = torch.clamp(w, 0, maxq)
-    ref = (w - maxq // 2).half() * s
-
-    def _reshape(t):
-        return t.reshape((groupsize, -1, n)).permute(1, 0, 2).reshape((k, n)).contiguous()
-
-    ref = _reshape(ref)
-    w = _reshape(w)
-    s = s.reshape((-1, n)).contiguous()
+    """Random fp16 weight [k, n] quantised symmetrically to 4 bits per group of `groupsize` input features -- the helper the
+    reference's tests and integrations import from here (quantization/utils.py:8-51).  Returns, like the reference,
+    (original weight, nn.Linear holding the dequantised weight, scales [k/g, n], signed integer weight [k, n]); the integer
+    range keeps the reference's clamp to [0, 16] before the -8 shift."""
+    levels = 16
+    g = k if groupsize == -1 else groupsize
+    original_w = torch.randn((k, n), dtype=torch.half, device="cpu")
+    grouped = original_w.view(k // g, g, n)
+    scales = grouped.abs().amax(dim=1, keepdim=True) * (2 / levels)              # [k/g, 1, n]
+    signed = torch.clamp(torch.round(grouped / scales).int() + levels // 2, 0, levels) - levels // 2
     linear = nn.Linear(k, n, bias=False)
-    linear.weight.data = ref.t()
-    return original_w, linear, s, (w - maxq // 2)
+    linear.weight.data = (signed.half() * scales).view(k, n).t()
+    return original_w, linear, scales.view(k // g, n).contiguous(), signed.view(k, n)
 
 
 def general_compress(lowprecision_weight, source_bits=4, storage_dtype=np.int8):

@@ -90,8 +90,10 @@ typedef enum bb_kernel_id {
   BB_KERNEL_GEMV_I8 = 3,   /* m <= 32, int8 A, 4/2-bit W: IMMA streaming, int32 exact         */
   BB_KERNEL_GEMM_TS = 4,   /* tcgen05 (W dequantised into TMEM as the MMA A operand) + TMA    */
   BB_KERNEL_GEMM_TS_I8 = 5,/* tcgen05 kind::i8 variant                                        */
-  BB_KERNEL_GEMV_STREAMK = 6 /* m <= 2, 4-bit W: persistent stream-K + TMA rings; opt-in through
+  BB_KERNEL_GEMV_STREAMK = 6,/* m <= 2, 4-bit W: persistent stream-K + TMA rings; opt-in through
                               * bb_set_kernel_override only (measured no faster than GEMV_MMA) */
+  BB_KERNEL_GEMV_SLAB = 7    /* m == 1, 4-bit W, fp16/bf16 A: per-CTA TMA slabs + CTA-level stream-K; the default
+                              * decode kernel (needs the zero-initialised workspace of bb_workspace_bytes) */
 } bb_kernel_id;
 
 /* replaces `init()` (builder/wrapper/base.py:5-13): one-time per-device setup (opt-in shared memory
@@ -119,7 +121,10 @@ int bb_matmul_scatter(const bb_matmul_desc* desc, const void* A, const void* W, 
                       int64_t col_offset, int m, void* workspace, size_t workspace_bytes, void* stream);
 
 /* scratch (fp32 split-K partials; stream-K slots + flags) the chosen kernel needs for this (desc, m); 0 for most configs.
- * Contents may be undefined on entry. */
+ * The buffer must be ZERO-INITIALISED once by the caller before its first use (cudaMemset / torch.zeros): the stream-K
+ * kernels exchange partial sums through tagged slots and leave every slot zero-tagged again when they finish, so the same
+ * buffer can then be reused by later calls ON THE SAME STREAM without clearing (calls that may run concurrently need their
+ * own buffers).  The split-K partials of the tcgen05 kernel carry no such requirement. */
 size_t bb_workspace_bytes(const bb_matmul_desc* desc, int m);
 
 /* which kernel family bb_matmul would run for (desc, m) -- bb_kernel_id; <0 on invalid desc. */
@@ -159,6 +164,14 @@ int bb_repack_gptq_qzeros_device(const int32_t* qzeros_gptq, const void* scales,
  * that compare against the reference's device decode functions (oracle/ref_shim.cu). ---- */
 int bb_debug_decode(int kind, int bits, int is_signed, int w_layout, const void* in, void* out, int ngroups,
                     void* stream);
+
+/* test hook: the tensor-core GEMM path's dequantise arithmetic -- decode, then ((w - zp) [- z]) * s in A_dtype with the
+ * reference's rounding order (bitblas/gpu/intrin/lop3.py:172-175,256,269) -- over an array of packed 32-bit words.
+ * kind: 0 = f16, 1 = bf16; mode: 0 none, 1 scale, 2 zeros "original", 3 zeros "rescale", 4 quantized zeros (qzeros: int32).
+ * One (scale, zeros, qzeros) entry per group of 8 outputs, like the reference's decode_*_scale[_zeros_*] device functions
+ * (testing/cpp/lop3_type_conversion/fast_decoding.hpp), which tests/test_gpu_decode_kat.py runs side by side. */
+int bb_debug_dequant(int kind, int bits, int is_signed, int w_layout, int mode, const void* in, const void* scale,
+                     const void* zeros, const void* qzeros, void* out, int nwords, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,7 +78,7 @@ def test_matmul_surface_and_dispatch():
                  "group_size", "fast_decoding", "with_bias", "propagate_a", "propagate_b", "layout", "zeros_mode"):
         assert getattr(op, name) == getattr(cfg, name)
     assert op.hardware_aware_finetune(topk=20) is None
-    assert [op.kernel_for(m) for m in (1, 8, 9, 32, 128, 4096)] == ["gemv_mma"] * 2 + ["gemm_ts_tcgen05"] * 4
+    assert [op.kernel_for(m) for m in (1, 8, 9, 32, 128, 4096)] == ["gemv_slab", "gemv_mma"] + ["gemm_ts_tcgen05"] * 4
     assert "gemm_ts_tcgen05" in op.get_source()
     # W2A8 (integration/BitNet/utils_quant.py:55-69)
     op8 = bitblas.Matmul(bitblas.MatmulConfig(M=[1, 128], N=12288, K=12288, A_dtype="int8", W_dtype="int2", accum_dtype="int32",
