@@ -56,13 +56,23 @@ class ColumnParallelLinear(nn.Module):
     """y = gather_N( x @ dequant(W_r)^T (+ b_r) ) with W sharded by rows (output features) across the group."""
 
     def __init__(self, in_features: int, out_features: int, *, process_group=None, gather_output: bool = True,
-                 pipeline_chunks: Optional[int] = None, fused_gather: Optional[bool] = None, **linear_kwargs):
+                 pipeline_chunks: Optional[int] = None, fused_gather: Optional[bool] = None, fused_ring: int = 2,
+                 clone_output: bool = False, **linear_kwargs):
         super().__init__()
         # fused_gather: the matmul kernel's epilogue stores this rank's column slice straight into every rank's output
         # (peer-mapped symmetric memory over NVLink/NVSwitch) -- no separate collective, the transfer overlaps the math
-        # tile by tile.  None = use it when torch symmetric memory is available on CUDA, else NCCL all-gather.
+        # tile by tile.  None = decided COLLECTIVELY at the first CUDA forward (every rank must be able to use it, else all
+        # ranks take the NCCL all-gather; a rank-local choice would leave peers waiting in a rendezvous / barrier).
+        # LIFETIME of the fused result: forward() returns a view into a ring of `fused_ring` symmetric buffers; it stays
+        # valid until `fused_ring - 1` further forward() calls of this layer have been issued (the call after that lets the
+        # peers overwrite it).  Pass clone_output=True (one extra copy) or a deeper ring to hold results longer.
+        if fused_ring < 2:
+            raise ValueError("fused_ring must be >= 2 (a rank may only overwrite a buffer after the next call's barrier)")
         self.fused_gather = fused_gather
-        self._symm = {}       # (rows capacity, dtype) -> [two (tensor, handle) pairs, next index]
+        self.fused_ring = int(fused_ring)
+        self.clone_output = bool(clone_output)
+        self._fused_decided = fused_gather is False
+        self._symm = {}       # (rows capacity, dtype) -> [ring of (tensor, handle, peer pointer array), next index]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
@@ -103,7 +113,7 @@ class ColumnParallelLinear(nn.Module):
         key = (cap, dtype)
         if key not in self._symm:
             pairs = []
-            for _ in range(2):  # double buffered: one barrier per call is enough (see forward)
+            for _ in range(self.fused_ring):  # ring: one barrier per call is enough (see _forward_fused)
                 t = symm_mem.empty((cap, self.out_features), dtype=dtype, device=device)
                 h = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
                 ptrs = [int(p) for p in h.buffer_ptrs]
@@ -112,7 +122,7 @@ class ColumnParallelLinear(nn.Module):
             self._symm[key] = [pairs, 0]
         entry = self._symm[key]
         t, h, arr = entry[0][entry[1]]
-        entry[1] ^= 1
+        entry[1] = (entry[1] + 1) % self.fused_ring
         return t, h, arr
 
     def _forward_fused(self, x2: torch.Tensor) -> torch.Tensor:
@@ -128,22 +138,40 @@ class ColumnParallelLinear(nn.Module):
         # a rank can only overwrite buffer b again after the NEXT call's barrier, which every peer reaches after its
         # (stream-ordered) reads of this call's result.
         hdl.barrier(channel=0)
-        return buf[:m]
+        return buf[:m].clone() if self.clone_output else buf[:m]
+
+    def _fused_supported_here(self, x2: torch.Tensor) -> bool:
+        """can THIS rank run the fused path for this call: symmetric memory importable and a kernel family with the scatter
+        epilogue (everything but the generic SIMT kernel) dispatched for this m."""
+        if not x2.is_cuda or self.local.consistent:
+            return False
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+        except Exception:
+            return False
+        return self.local.bitblas_matmul.kernel_for(int(x2.shape[0])) != "generic_simt"
+
+    def _decide_fused(self, x2: torch.Tensor) -> None:
+        """one collective decision per layer (MIN over ranks of the local capability), taken at the first CUDA forward."""
+        ok = torch.tensor([1 if self._fused_supported_here(x2) else 0], dtype=torch.int32, device=x2.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        agreed = bool(int(ok.item()))
+        if self.fused_gather is True and not agreed:
+            raise RuntimeError("fused_gather=True was requested but at least one rank cannot use it")
+        self.fused_gather = agreed
+        self._fused_decided = True
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.world == 1 or not self.gather_output:
             return self.local(x)
-        if x.is_cuda and self.fused_gather is not False and not self.local.consistent:
-            try:
-                out = self._forward_fused(x.reshape(-1, x.shape[-1]))
-                self.fused_gather = True
-                return out.reshape(*x.shape[:-1], self.out_features)
-            except Exception as e:  # symmetric memory unavailable / kernel family without a scatter epilogue
-                if self.fused_gather is True:
-                    raise
-                import logging
-                logging.getLogger(__name__).warning("fused column-parallel gather unavailable (%s); using NCCL all-gather", e)
-                self.fused_gather = False
+        if x.is_cuda and not self._fused_decided:
+            self._decide_fused(x.reshape(-1, x.shape[-1]))
+        if x.is_cuda and self.fused_gather:
+            x2 = x.reshape(-1, x.shape[-1])
+            # per-call probe (the dispatcher's choice depends on m): an m that lands on the generic kernel takes the NCCL path
+            # for this call only -- identically on every rank, since all ranks see the same m and the same shard shape
+            if self.local.bitblas_matmul.kernel_for(int(x2.shape[0])) != "generic_simt":
+                return self._forward_fused(x2).reshape(*x.shape[:-1], self.out_features)
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         m = x2.shape[0]

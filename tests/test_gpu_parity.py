@@ -379,3 +379,48 @@ def test_gptq_repack_device_matches_reference_loops():
         ref = O.matmul_dequant(A, fields, W_dtype="uint4", group_size=g, with_scaling=True, with_zeros=True,
                                zeros_mode=mode, scale=scales.T.contiguous(), zeros=lin.zeros.cpu())
         H.assert_fp_close(lin(A.cuda()).cpu(), ref, f"gptq-{mode}")
+
+
+@pytest.mark.parametrize("bits", [4, 2])
+@pytest.mark.parametrize("m", [1, 16])
+def test_gptq_repack_v2_module(bits, m):
+    """Linear.repack_from_gptq_v2 (bitblas/module/__init__.py:340-363; testing/python/module/test_repack_from_gptq_v2.py): the
+    v2 checkpoint format stores the zero point itself (no +1, unpack_qzeros_v2 :43-58).  A synthetic GPTQ module (int32-packed
+    qweight [K*bits/32, N], qzeros [K/g, N*bits/32], scales [K/g, N], bias) is repacked on the device for every zeros mode and
+    the module output is compared with the dequantised dense layer, m = 1 (GEMV) and m = 16 (tensor-core path)."""
+    import bitblas_oracle as O
+    import bitblas_b200 as bitblas
+    torch.manual_seed(1)
+    K, N, g = 1024, 512, 128
+    per = 32 // bits
+    intw = torch.randint(0, 2**bits, (K, N), dtype=torch.int32)
+    qweight = torch.zeros((K // per, N), dtype=torch.int32)
+    for k in range(K):
+        qweight[k // per] |= intw[k] << (bits * (k % per))
+    zint = torch.randint(0, 2**bits, (K // g, N), dtype=torch.int32)   # v2: the full range is representable
+    qzeros = torch.zeros((K // g, N // per), dtype=torch.int32)
+    for n in range(N):
+        qzeros[:, n // per] |= zint[:, n] << (bits * (n % per))
+    scales = (torch.rand(K // g, N) * 0.1 + 0.01).half()
+    bias = torch.rand(N).half()
+
+    class G:
+        pass
+    gm = G(); gm.qweight = qweight; gm.qzeros = qzeros; gm.scales = scales
+    gm.bias = torch.nn.Parameter(bias.clone(), requires_grad=False)
+    dense = ((intw.T.float() - zint.T.repeat_interleave(g, dim=1).float()) * scales.T.repeat_interleave(g, dim=1).float())   # [N, K]
+    A = (torch.rand(m, K) - 0.5).half()
+    ref = (A.float() @ dense.t() + bias.float()).half()
+    assert torch.equal(O.unpack_qzeros(qzeros, bits, v2=True).T.contiguous(), zint.T.contiguous().to(torch.int8))
+    for mode in ("original", "rescale", "quantized"):
+        lin = bitblas.Linear(K, N, bias=True, A_dtype="float16", W_dtype=f"uint{bits}", group_size=g, with_scaling=True,
+                             with_zeros=True, zeros_mode=mode, enable_tuning=False).cuda()
+        lin.repack_from_gptq_v2(gm)
+        fields = intw.T.contiguous()
+        assert torch.equal(lin.qweight.cpu(), O.transform_weight(fields.to(torch.int8), f"uint{bits}", "float16", fast_decoding=True))
+        if mode == "original":
+            assert torch.equal(lin.zeros.cpu(), zint.T.contiguous().half())
+        elif mode == "quantized":
+            assert torch.equal(lin.zeros.cpu(), torch.from_numpy(O.general_compress(zint.to(torch.int8).numpy(), bits)))
+        got = lin(A.cuda()).cpu()
+        H.assert_fp_close(got, ref, f"gptq-v2 {mode} bits={bits} m={m}")

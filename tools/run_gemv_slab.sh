@@ -5,7 +5,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpur
 echo "== small shape sanity" >> gpurun_out/r2_slab_bench.txt
 timeout 120 tools/gemv_bench --iters 20 1024x2048 4112x6144 >> gpurun_out/r2_slab_bench.txt 2>&1 || echo "SANITY FAILED rc=$?" >> gpurun_out/r2_slab_bench.txt
 echo "== sweep" >> gpurun_out/r2_slab_bench.txt
-timeout 300 tools/gemv_bench --iters 200 --cfg 4,2 --cfg 3,2 --cfg 3,3 --cfg 6,1 --cfg 2,2 --cfg 2,3 12288x12288 8192x8192 28672x8192 8192x28672 >> gpurun_out/r2_slab_bench.txt 2>&1 || echo "SWEEP FAILED rc=$?" >> gpurun_out/r2_slab_bench.txt
+timeout 300 tools/gemv_bench --iters 200 --cfg 4,2 --cfg 3,2 --cfg 3,3 --cfg 6,1 --cfg 2,2 12288x12288 8192x8192 28672x8192 8192x28672 >> gpurun_out/r2_slab_bench.txt 2>&1 || echo "SWEEP FAILED rc=$?" >> gpurun_out/r2_slab_bench.txt
 echo "== no PDL" >> gpurun_out/r2_slab_bench.txt
 BB_PDL=0 timeout 120 tools/gemv_bench --iters 200 --nocheck --cfg 4,2,-1 12288x12288 8192x8192 >> gpurun_out/r2_slab_bench.txt 2>&1
 echo "== old kernel (gemv_mma)" >> gpurun_out/r2_slab_bench.txt
