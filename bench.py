@@ -6,15 +6,18 @@
 One "step" = one pass of the hot path over the workload `w4a16_gemv_llama70b`: the W4A16 (uint4, group 128, GPTQ-style
 quantized zeros, interleaved storage) GEMV at M=1 for the Llama-2-70B linear shapes BASELINE.json configs[1] names
 ((N,K) = (8192,8192), (28672,8192), (8192,28672)) plus the target shape (12288,12288).  `value` = algorithmic bytes of
-the step / device time (GB/s), inputs resident in HBM.  The compute-bound half of the metric (W4A16 GEMM M=4096,
-N=K=12288, TFLOPS) and the W2A8 path are measured in the same run and reported under "gemm" / "w2a8" with their own
-roofline objects.  `e2e` goes through the public operator API with HOST activations (pinned H2D copy + D2H of the result
-inside the timed region, synchronised every step).  With --gpus N>1 (launched under torchrun) the weights are sharded
-along N across ranks (column parallel) and the outputs all-gathered: strong scaling, max-over-ranks device time.
+the step / device time (GB/s), inputs resident in HBM.  Before anything is timed, one shape is built from REAL quantised
+fields through the product's own weight transform and a slice of its output is checked against the CPU oracle (a kernel
+that is wrong at scale must not post a number).  The compute-bound half of the metric (W4A16 GEMM, M in {16,128,4096} on
+the three Llama (N,K) pairs + M=4096 N=K=12288, TFLOPS) and the W2A8 path are measured in the same run and reported under
+"gemm" / "gemm_llama" / "w2a8" with their own roofline objects.  `e2e` goes through the public operator API with HOST
+activations (pinned H2D copy + D2H of the result inside the timed region, synchronised every step).  With --gpus N>1
+(launched under torchrun) the weights are sharded along N across ranks (column parallel) and the outputs gathered:
+strong scaling, max-over-ranks device time.
 
 --impl reference times the reference's only CPU implementation of this path -- the torch dequantise+matmul reference
 program of its tests (testing/python/operators/test_general_matmul_ops_backend_tl.py:227-273), restated in
-oracle/bitblas_oracle.py -- on the host cores, on a bounded sample of the same workload.
+oracle/bitblas_oracle.py -- on the host cores, on a bounded row sample of the SAME four shapes.
 """
 from __future__ import annotations
 
@@ -36,6 +39,10 @@ sys.path.insert(0, ROOT)
 GEMV_SHAPES = [(8192, 8192), (28672, 8192), (8192, 28672), (12288, 12288)]  # (N, K)
 GROUP = 128
 GEMM_SHAPE = (4096, 12288, 12288)  # (M, N, K)
+LLAMA_NK = [(8192, 8192), (28672, 8192), (8192, 28672)]
+# the workload both arms are run on; identical in both JSON lines (everything arm-specific lives under other keys)
+CONFIG = {"workload": "w4a16_gemv_llama70b", "shapes_NK": GEMV_SHAPES, "M": 1, "A_dtype": "float16", "W_dtype": "uint4",
+          "group_size": GROUP, "zeros_mode": "quantized"}
 
 
 def peaks():
@@ -44,6 +51,16 @@ def peaks():
         d = json.load(open(p))
         return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained"), src="measured (MEASURED_PEAKS.json)")
     return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def profiled_traffic():
+    """DRAM bytes per launch of the dominant kernels, from the committed ncu capture (profiles/r2_traffic.json, written by
+    tools/ncu_traffic.py out of an `ncu --set full` report; keyed to the commit it was taken at).  None if absent."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def gemv_bytes(N, K, M=1, bits=4, g=GROUP, zeros="quantized", a_bytes=2, out_bytes=2):
@@ -122,58 +139,77 @@ def pick_cpu_threads():
     return best
 
 
-def cpu_reference_gemv(N, K, reps, warmup=1):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import bitblas_oracle as O
-    import numpy as np
-    cores = pick_cpu_threads()
-    torch.set_num_threads(cores)
-    g = torch.Generator().manual_seed(0)
-    fields = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int32)
-    scale = (torch.rand((N, K // GROUP), generator=g) * 0.1 + 0.01).half()
-    zq = torch.randint(0, 16, (K // GROUP, N), generator=g, dtype=torch.int8)
-    qz = torch.from_numpy(O.general_compress(zq.numpy(), 4))
-    A = (torch.rand((1, K), generator=g) - 0.5).half()
+class CpuWorkload:
+    """The reference's CPU computation of the workload: for each of the four shapes a ROW SAMPLE (the first N/sample_div output
+    features -- rows of W are independent dot products, so the GB/s of a row sample is the GB/s of the shape) of the
+    un-packed int weight matrix, (w - z) * s in fp16, fp32 matmul (test_general_matmul_ops_backend_tl.py:227-273)."""
 
-    # like the reference's test program (test_general_matmul_ops_backend_tl.py:227-273) the CPU path works on the
-    # un-packed int weight matrix [N, K]; only the quantized zeros are unpacked inside the step
-    def step():
-        return O.matmul_dequant(A, fields, W_dtype="uint4", group_size=GROUP, with_scaling=True, with_zeros=True,
-                                zeros_mode="quantized", scale=scale, zeros=qz)
+    def __init__(self, sample_div=16, cores=None):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import bitblas_oracle as O
+        self.O = O
+        self.cores = cores or pick_cpu_threads()
+        torch.set_num_threads(self.cores)
+        self.sample_div = sample_div
+        g = torch.Generator().manual_seed(0)
+        self.cases = []
+        self.bytes = 0
+        for N, K in GEMV_SHAPES:
+            n = max(16, N // sample_div)
+            fields = torch.randint(0, 16, (n, K), generator=g, dtype=torch.int32)
+            scale = (torch.rand((n, K // GROUP), generator=g) * 0.1 + 0.01).half()
+            zq = torch.randint(0, 16, (K // GROUP, n), generator=g, dtype=torch.int8)
+            qz = torch.from_numpy(O.general_compress(zq.numpy(), 4))
+            A = (torch.rand((1, K), generator=g) - 0.5).half()
+            self.cases.append((A, fields, scale, qz))
+            self.bytes += gemv_bytes(n, K)
 
-    for _ in range(warmup):
-        step()
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        step()
-        ts.append(time.perf_counter() - t0)
-    t = statistics.median(ts)
-    # context: the north star's "torch.matmul FP16 CPU path" alone, on a pre-dequantised fp16 weight matrix
-    Wd = O.dequantize_weight(fields, W_dtype="uint4", group_size=GROUP, with_scaling=True, with_zeros=True,
+    def step(self):
+        O = self.O
+        for A, fields, scale, qz in self.cases:
+            O.matmul_dequant(A, fields, W_dtype="uint4", group_size=GROUP, with_scaling=True, with_zeros=True,
                              zeros_mode="quantized", scale=scale, zeros=qz)
-    torch.matmul(A, Wd.T)
-    t0 = time.perf_counter()
-    for _ in range(3):
-        torch.matmul(A, Wd.T)
-    t_mm = (time.perf_counter() - t0) / 3
-    return dict(value=gemv_bytes(N, K) / t / 1e9, unit="GB/s", cores=cores, kind="port", matmul_fp16_only_ms=round(t_mm * 1e3, 3),
-                sample=f"W4A16 GEMV M=1 N={N} K={K} g={GROUP} quantized zeros: torch (w-z)*s in fp16 + fp32 matmul on the int weight matrix, "
-                       f"median of {reps} reps, {t * 1e3:.1f} ms/rep", ms_per_step=t * 1e3)
+
+    def matmul_fp16_only_ms(self):
+        """context: the north star's "torch.matmul FP16 CPU path" alone, on pre-dequantised fp16 weights (same row sample)."""
+        O = self.O
+        ws = [(A, O.dequantize_weight(f, W_dtype="uint4", group_size=GROUP, with_scaling=True, with_zeros=True,
+                                      zeros_mode="quantized", scale=s, zeros=z)) for A, f, s, z in self.cases]
+        for A, Wd in ws:
+            torch.matmul(A, Wd.T)
+        ts = []
+        for _ in range(10):   # BASELINE.md §3: 10 timed reps, median
+            t0 = time.perf_counter()
+            for A, Wd in ws:
+                torch.matmul(A, Wd.T)
+            ts.append(time.perf_counter() - t0)
+        return statistics.median(ts) * 1e3
+
+    def describe(self, ms):
+        return (f"row sample 1/{self.sample_div} of each of the 4 shapes {GEMV_SHAPES} (M=1, g={GROUP}, quantized zeros): torch "
+                f"(w-z)*s in fp16 + fp32 matmul on the int weight matrix, {ms:.1f} ms per sampled pass, {self.cores} threads")
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    N, K = 8192, 8192
-    r = cpu_reference_gemv(N, K, reps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
-    line = {"metric": "w4a16_gemv_gbps_llama70b", "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "w4a16_gemv_llama70b", "sample": r["sample"]},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    wl = CpuWorkload()
+    for _ in range(max(1, min(args.warmup, 3))):
+        wl.step()
+    ts = []
+    for _ in range(max(1, args.steps)):
+        t0 = time.perf_counter()
+        wl.step()
+        ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    value = wl.bytes / t / 1e9
+    sample = wl.describe(t * 1e3)
+    line = {"metric": "w4a16_gemv_gbps_llama70b", "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference", "config": CONFIG,
+            "cpu_baseline": {"value": value, "unit": "GB/s", "cores": wl.cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -204,6 +240,40 @@ def make_linear(bitblas, N_local, K, dev, *, a_dtype="float16", w_dtype="uint4",
     return op, dict(W=W, scale=scale, zeros=zeros)
 
 
+def oracle_gate(bitblas, dev):
+    """Correctness gate, run before any timing: W4A16 at a BASELINE shape built from real quantised fields through the product's
+    own device weight transform; M = 1 (the streaming kernel) and M = 16 (the tcgen05 kernel); 512 output features compared with
+    the CPU oracle (rtol = atol = 1e-2 like the reference's tests).  Raises on mismatch."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bitblas_oracle as O
+    N, K, ncheck = 8192, 8192, 512
+    g = torch.Generator().manual_seed(123)
+    fields = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int8)
+    scale = (torch.rand((N, K // GROUP), generator=g) * 0.1 + 0.01).half()
+    zq = torch.randint(0, 16, (K // GROUP, N), generator=g, dtype=torch.int8)
+    qz = torch.from_numpy(O.general_compress(zq.numpy(), 4))
+    cfg = bitblas.MatmulConfig(M=[1, 16], N=N, K=K, A_dtype="float16", W_dtype="uint4", accum_dtype="float16", out_dtype="float16",
+                               group_size=GROUP, with_scaling=True, with_zeros=True, zeros_mode="quantized")
+    op = bitblas.Matmul(cfg, enable_tuning=False)
+    W = op.transform_weight(fields.to(dev))
+    sc, zz = scale.to(dev), qz.to(dev)
+    report = {}
+    for m in (1, 16):
+        A = (torch.rand((m, K), generator=g) - 0.5).half()
+        got = op.forward(A.to(dev), W, scale=sc, zeros=zz).cpu()
+        # the last `ncheck` output features (rows of W): scale rows and the matching packed-zero columns
+        ref = O.matmul_dequant(A, fields[N - ncheck:].to(torch.int32), W_dtype="uint4", group_size=GROUP, with_scaling=True,
+                               with_zeros=True, zeros_mode="quantized", scale=scale[N - ncheck:],
+                               zeros=torch.from_numpy(O.general_compress(zq[:, N - ncheck:].numpy(), 4)))
+        err = O.rel_fro_error(got[:, N - ncheck:], ref)
+        O.torch_assert_close(got[:, N - ncheck:].float(), ref.float(), rtol=1e-2, atol=1e-2 * max(1.0, float(ref.float().abs().mean())),
+                             max_mismatched_ratio=0.0)
+        if not (err <= 1e-2):
+            raise AssertionError(f"oracle gate failed: m={m} normwise rel err {err}")
+        report[f"m{m}"] = {"kernel": op.kernel_for(m), "rel_fro_err": float(f"{err:.3e}")}
+    return {"shape_NK": [N, K], "features_checked": ncheck, "criterion": "normwise <= 1e-2 and elementwise rtol=atol=1e-2, 0 mismatches", **report}
+
+
 def timed(fn, steps, warmup, barrier=None):
     for _ in range(warmup):
         fn()
@@ -221,8 +291,50 @@ def timed(fn, steps, warmup, barrier=None):
     return s.elapsed_time(e) / steps  # ms per step
 
 
-def flush_l2(buf):
-    buf.add_(1)
+def rotating_kernel_time(op, prm, A, out, reps=5, min_bytes=300 * 1024 * 1024):
+    """per-launch kernel time with a cold L2: back-to-back launches cycling through enough read-only copies of the parameters
+    that the working set (> 2x the 126 MB L2) can never be resident; median of `reps` passes.  (No write-flush: dirty lines
+    left in L2 by a flush kernel are written back DURING the timed kernel and charged to it -- measured +10..25 us.)"""
+    wbytes = prm["W"].numel()
+    ncopies = max(2, -(-min_bytes // wbytes))
+    copies = [prm] + [{k: (v.clone() if v is not None else None) for k, v in prm.items()} for _ in range(ncopies - 1)]
+    for c in copies:
+        op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(2 * ncopies):
+            c = copies[i % ncopies]
+            op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) / (2 * ncopies))
+    return statistics.median(ts), ncopies
+
+
+def int8_peak_tops(dev):
+    """dense int8 tensor-core throughput of this GPU through cuBLASLt (torch._int_mm, 8192^3), burst: the denominator of the
+    W2A8 GEMM fraction (MEASURED_PEAKS.json has no int8 entry)."""
+    try:
+        a = torch.randint(-128, 128, (8192, 8192), dtype=torch.int8, device=dev)
+        b = torch.randint(-128, 128, (8192, 8192), dtype=torch.int8, device=dev).t()
+        for _ in range(3):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch._int_mm(a, b)
+            e.record()
+            torch.cuda.synchronize()
+            t = s.elapsed_time(e)
+            best = t if best is None or t < best else best
+        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def main():
@@ -232,7 +344,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--only", default="", help="comma list of sections to run: gemv,gemm,w2a8,e2e (default all)")
+    ap.add_argument("--only", default="", help="comma list of sections to run: gemm,llama,w2a8,e2e (default all; the GEMV step always runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -251,8 +363,10 @@ def main():
     from bitblas_b200 import _lib
     lib = _lib.load()
     pk = peaks()
+    traffic = profiled_traffic()
     only = set(x for x in args.only.split(",") if x)
     want = lambda s: not only or s in only  # noqa: E731
+    warmup = max(3, args.warmup)
 
     def barrier():
         if world > 1:
@@ -272,6 +386,9 @@ def main():
         g = torch.empty((world * m, out_local.shape[-1]), dtype=out_local.dtype, device=dev)
         dist.all_gather_into_tensor(g, out_local)
         return g
+
+    # ---- correctness gate (rank 0 checks; every rank must pass before anything is timed) ----
+    gate = oracle_gate(bitblas, dev)
 
     # fused flavour: the kernel epilogue stores this rank's column slice into every rank's output (symmetric memory over
     # NVLink), then one device-side barrier -- no separate collective (bb_matmul_scatter)
@@ -326,7 +443,7 @@ def main():
         op.forward(A, prm["W"], scale=prm["scale"], zeros=prm["zeros"], output=out_local)
         return gather(out_local, m)
 
-    result = {}
+    result = {"oracle_gate": gate}
     sampler = ClockSampler(torch.cuda.current_device())
     # ---------------- GEMV (the headline workload) ----------------
     ops = []
@@ -346,98 +463,92 @@ def main():
         if pending:
             pending[-1].barrier(channel=0)   # peer stores of all four projections precede it in stream order on every rank
 
-    launches0 = lib.bb_launch_count()
     if rank == 0:
         sampler.start()
-    ms_step = timed(gemv_step, args.steps, max(3, args.warmup), barrier)
+    for _ in range(warmup):
+        gemv_step()
+    torch.cuda.synchronize()
+    launches0 = lib.bb_launch_count()
+    ms_step = timed(gemv_step, args.steps, 0, barrier)
+    launches = lib.bb_launch_count() - launches0      # kernels of this library launched inside the timed region
     ms_step = max_over_ranks(ms_step)
-    launches = (lib.bb_launch_count() - launches0) * args.steps // (args.steps + max(3, args.warmup))
     value = total_bytes / (ms_step * 1e-3) / 1e9
 
-    # per-shape kernel time, cold L2: the launch cycles through enough read-only copies of the parameters that the
-    # working set (> 2x the 126 MB L2) can never be resident; no write-flush is used because dirty lines left in L2 by a
-    # flush kernel get written back DURING the timed kernel and are charged to it (measured: +10..25 us).
+    # per-shape kernel time, cold L2 (rotating parameter copies)
     per_shape = []
-    flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
     for op, prm, A, out, N, K in ops:
-        wbytes = prm["W"].numel()
-        ncopies = max(2, -(-300 * 1024 * 1024 // wbytes))
-        copies = [prm] + [{k: (v.clone() if v is not None else None) for k, v in prm.items()} for _ in range(ncopies - 1)]
-        for c in copies:
-            op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
-        torch.cuda.synchronize()
-        # back-to-back launches (no idle-stream launch latency between the events), one pass = every copy once
-        ts = []
-        for _ in range(5):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for i in range(2 * ncopies):
-                c = copies[i % ncopies]
-                op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
-            e.record()
-            torch.cuda.synchronize()
-            ts.append(s.elapsed_time(e) / (2 * ncopies))
-        t = statistics.median(ts)
+        t, ncopies = rotating_kernel_time(op, prm, A, out)
         b = gemv_bytes(N // world, K)
         per_shape.append({"N": N, "K": K, "us": round(t * 1e3, 2), "GBps": round(b / (t * 1e-3) / 1e9, 1),
                           "frac_hbm": round(b / (t * 1e-3) / 1e9 / pk["hbm"], 3), "kernel": op.kernel_for(1), "copies": ncopies})
-        del copies
     tgt = per_shape[-1]
-    roofline = {"bound": "hbm", "kernel": "gemv_mma_kernel<half,4,interleaved,NT=1> N=K=12288", "achieved": tgt["GBps"],
+    tr = traffic.get("gemv_m1_12288") if world == 1 else None
+    roofline = {"bound": "hbm", "kernel": f"{tgt['kernel']} (W4A16 m=1 N=K=12288)", "achieved": tgt["GBps"],
                 "peak": pk["hbm"], "unit": "GB/s", "frac": tgt["frac_hbm"],
-                "traffic": 80.75e6 if world == 1 else None,  # dram read+write per launch (78.51 + 2.24 MB), profiles/r1_gemv_mma_ncu_full.txt
+                "traffic": tr.get("dram_bytes") if tr else None, "traffic_source": tr.get("source") if tr else None,
                 "algorithmic_bytes": gemv_bytes(12288 // world, 12288), "us": tgt["us"], "peak_source": pk["src"],
                 "timing": "CUDA events around back-to-back launches cycling through >= 300 MB of read-only parameter copies (cold L2), per-launch average, median of 5"}
     result["gemv_shapes"] = per_shape
 
-    # ---------------- GEMM M=4096 (tensor-bound half of the metric) ----------------
+    def gemm_point(op, prm, m, N, K, reps):
+        A = (torch.rand((m, K), device=dev) - 0.5).half()
+        out = torch.empty((m, N // world), dtype=torch.float16, device=dev)
+        ms = max_over_ranks(timed(lambda: run_sharded(op, prm, A, out, m, N), reps, 3, barrier))
+        tf = 2.0 * m * N * K / (ms * 1e-3) / 1e12
+        b = gemv_bytes(N, K, M=m)
+        t_mem, t_fl = b / (pk["hbm"] * 1e9), 2.0 * m * N * K / (pk["tf"] * 1e12)
+        return {"M": m, "N": N, "K": K, "us": round(ms * 1e3, 2), "TFLOPS": round(tf, 1), "GBps": round(b / (ms * 1e-3) / 1e9, 1),
+                "frac_tensor": round(tf / pk["tf"], 3), "frac_of_max_roofline": round(max(t_mem, t_fl) / (ms * 1e-3), 3),
+                "kernel": op.kernel_for(m)}
+
+    # ---------------- GEMM M=4096 N=K=12288 (tensor-bound half of the metric) + small M ----------------
     if want("gemm"):
         M, N, K = GEMM_SHAPE
         op, prm = make_linear(bitblas, N // world, K, dev, seed=11)
-        A = (torch.rand((M, K), device=dev) - 0.5).half()
-        out = torch.empty((M, N // world), dtype=torch.float16, device=dev)
-
-        def gemm_step():
-            run_sharded(op, prm, A, out, M, N)
-
-        ms = max_over_ranks(timed(gemm_step, 10, 3, barrier))
-        tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
-        result["gemm"] = {"M": M, "N": N, "K": K, "ms": round(ms, 4), "TFLOPS": round(tf, 1), "kernel": op.kernel_for(M),
-                          "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": pk["tf"], "unit": "TFLOP/s",
-                                       "frac": round(tf / pk["tf"], 3), "frac_of_sustained": round(tf / pk["tf_sustained"], 3) if pk["tf_sustained"] else None,
-                                       "traffic": 1274.2e6 if world == 1 else None,  # dram read+write (1173.4 + 100.8 MB), profiles/r1_gemm_ts_ncu_full.txt
+        g4 = gemm_point(op, prm, M, N, K, 10)
+        trg = traffic.get("gemm_m4096_12288") if world == 1 else None
+        result["gemm"] = {"M": M, "N": N, "K": K, "ms": round(g4["us"] / 1e3, 4), "TFLOPS": g4["TFLOPS"], "kernel": g4["kernel"],
+                          "roofline": {"bound": "tensor", "achieved": g4["TFLOPS"], "peak": pk["tf"], "unit": "TFLOP/s",
+                                       "frac": g4["frac_tensor"],
+                                       "frac_of_sustained": round(g4["TFLOPS"] / pk["tf_sustained"], 3) if pk["tf_sustained"] else None,
+                                       "traffic": trg.get("dram_bytes") if trg else None, "traffic_source": trg.get("source") if trg else None,
                                        "algorithmic_flops": 2.0 * M * N * K, "peak_source": pk["src"],
                                        "note": "A (100 MB) + W (75 MB) exceed L2; 10 back-to-back launches"}}
-        small = []
-        for m in (16, 128):
-            A2 = (torch.rand((m, K), device=dev) - 0.5).half()
-            out2 = torch.empty((m, N // world), dtype=torch.float16, device=dev)
-            ms2 = max_over_ranks(timed(lambda: run_sharded(op, prm, A2, out2, m, N), 20, 3, barrier))
-            b = gemv_bytes(N, K, M=m)
-            t_mem, t_fl = b / (pk["hbm"] * 1e9), 2.0 * m * N * K / (pk["tf"] * 1e12)
-            small.append({"M": m, "us": round(ms2 * 1e3, 2), "TFLOPS": round(2.0 * m * N * K / (ms2 * 1e-3) / 1e12, 1),
-                          "GBps": round(b / (ms2 * 1e-3) / 1e9, 1), "frac_of_max_roofline": round(max(t_mem, t_fl) / (ms2 * 1e-3), 3),
-                          "kernel": op.kernel_for(m)})
-        result["gemm_small_m"] = small
-        del A, out, op, prm
+        result["gemm_small_m"] = [gemm_point(op, prm, m, N, K, 20) for m in (16, 128)]
+        del op, prm
 
-    # ---------------- W2A8 (BitNet) ----------------
+    # ---------------- BASELINE configs[2]: W4A16 GEMM M in {16,128,4096} on the three Llama-70B (N,K) pairs ----------------
+    if want("llama"):
+        rows = []
+        for i, (N, K) in enumerate(LLAMA_NK):
+            op, prm = make_linear(bitblas, N // world, K, dev, seed=30 + i)
+            for m in (16, 128, 4096):
+                rows.append(gemm_point(op, prm, m, N, K, 10 if m == 4096 else 20))
+            del op, prm
+        result["gemm_llama"] = rows
+
+    # ---------------- W2A8 (BitNet), same cold-L2 method as W4A16 ----------------
     if want("w2a8"):
         N, K = 12288, 12288
         op8, prm8 = make_linear(bitblas, N // world, K, dev, a_dtype="int8", w_dtype="int2", seed=21, M=(1, 128))
+        i8peak = int8_peak_tops(dev) if world == 1 else None
         w2 = []
         for m in (1, 128):
             A8 = torch.randint(-128, 128, (m, K), dtype=torch.int8, device=dev)
             out8 = torch.empty((m, N // world), dtype=torch.int32, device=dev)
-            ms8 = max_over_ranks(timed(lambda: (flush_l2(flush) if m == 1 else None, run_sharded(op8, prm8, A8, out8, m, N)), 20, 3, barrier))
-            if m == 1:  # subtract the flush cost measured alone
-                ms_f = timed(lambda: flush_l2(flush), 20, 3)
-                ms8 = max(ms8 - ms_f, 1e-4)
+            if world == 1:
+                t8, _ = rotating_kernel_time(op8, prm8, A8, out8)
+            else:
+                t8 = max_over_ranks(timed(lambda: run_sharded(op8, prm8, A8, out8, m, N), 20, 3, barrier))
             b = N * K // 4 + m * K + m * N * 4
-            w2.append({"M": m, "us": round(ms8 * 1e3, 2), "GBps": round(b / (ms8 * 1e-3) / 1e9, 1),
-                       "TOPS": round(2.0 * m * N * K / (ms8 * 1e-3) / 1e12, 1), "frac_hbm": round(b / (ms8 * 1e-3) / 1e9 / pk["hbm"], 3),
-                       "kernel": op8.kernel_for(m)})
+            tops = 2.0 * m * N * K / (t8 * 1e-3) / 1e12
+            row = {"M": m, "us": round(t8 * 1e3, 2), "GBps": round(b / (t8 * 1e-3) / 1e9, 1), "TOPS": round(tops, 1),
+                   "frac_hbm": round(b / (t8 * 1e-3) / 1e9 / pk["hbm"], 3), "kernel": op8.kernel_for(m)}
+            if i8peak:
+                row["frac_int8_peak"] = round(tops / i8peak, 4)
+            w2.append(row)
         result["w2a8"] = w2
+        result["int8_peak_tops_measured"] = round(i8peak, 1) if i8peak else None
 
     # ---------------- e2e: public API, host activations in, host results out, one sync per step ----------------
     e2e = None
@@ -453,7 +564,7 @@ def main():
                 hC.copy_(full, non_blocking=True)
             stream.synchronize()   # one host-visible result per step: all four projections' outputs are in pinned memory here
 
-        ms_e = max_over_ranks(timed(e2e_step, args.steps, max(3, args.warmup), barrier))
+        ms_e = max_over_ranks(timed(e2e_step, args.steps, warmup, barrier))
         e2e = {"value": round(total_bytes / (ms_e * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(ms_e, 4),
                "h2d_bytes_per_step": sum(K * 2 for _, K in GEMV_SHAPES), "d2h_bytes_per_step": sum(N * 2 for N, _ in GEMV_SHAPES),
                "note": "per step: 4 x (pinned H2D of the activations, Matmul.forward, D2H of the output into pinned memory), then ONE stream synchronise -- the host reads the step's results after it"}
@@ -461,17 +572,31 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu = cpu_reference_gemv(8192, 8192, reps=3, warmup=1)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "matmul_fp16_only_ms")}
-        cpu["value"] = round(cpu["value"], 4)
+        wl = CpuWorkload()
+        wl.step()
+        ts = []
+        for _ in range(10):   # 3 warm-ups (1 here: ~0.5 s each), 10 timed reps, median
+            t0 = time.perf_counter()
+            wl.step()
+            ts.append(time.perf_counter() - t0)
+        t = statistics.median(ts)
+        mm_ms = wl.matmul_fp16_only_ms()
+        cpu = {"value": round(wl.bytes / t / 1e9, 4), "unit": "GB/s", "cores": wl.cores, "kind": "port", "sample": wl.describe(t * 1e3),
+               "matmul_fp16_only_ms": round(mm_ms, 3),
+               "matmul_fp16_only_note": "the north star's torch.matmul-FP16 CPU path on PRE-dequantised fp16 weights, same row sample"}
+        # the two host-side ratios a reader wants next to the GPU number, on the same bytes: dequant+matmul and matmul only
+        gpu_ms_equiv = ms_step / wl.sample_div
+        result["vs_cpu"] = {"dequant_matmul_ratio": round(t * 1e3 / gpu_ms_equiv, 1), "matmul_fp16_only_ratio": round(mm_ms / gpu_ms_equiv, 1),
+                            "note": f"CPU time for a 1/{wl.sample_div} row sample of the step / (GPU step time / {wl.sample_div})"}
 
     if rank == 0:
+        par = (f"column-parallel x{world}, " + (("fused peer-store epilogue over NVLink (bb_matmul_scatter) + one device barrier per "
+               + ("step" if step_sync else "projection")) if fused["on"] else "NCCL all-gather")) if world > 1 else "single GPU"
         line = {"metric": "w4a16_gemv_gbps_llama70b", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                "config": {"workload": "w4a16_gemv_llama70b", "shapes_NK": GEMV_SHAPES, "M": 1, "W_dtype": "uint4", "group_size": GROUP,
-                           "zeros_mode": "quantized", "parallelism": (f"column-parallel x{world}, " + (("fused peer-store epilogue over NVLink (bb_matmul_scatter) + one device barrier per " + ("step" if step_sync else "projection")) if fused["on"] else "NCCL all-gather")) if world > 1 else "single GPU",
-                           "l2": "step working set 357 MB cycles through the 126 MB L2 (inputs larger than L2); per-shape numbers rotate >= 300 MB of parameter copies"},
+                "warmup": warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": CONFIG,
+                "config_detail": {"parallelism": par,
+                                  "l2": "step working set 357 MB cycles through the 126 MB L2 (inputs larger than L2); per-shape numbers rotate >= 300 MB of parameter copies"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         line.update(result)
         print(json.dumps(line), flush=True)

@@ -57,6 +57,8 @@ constexpr int GS_ROW_BYTES = GS_SLICE_BYTES * GS_NCONS;     // packed bytes per 
 constexpr int GS_WBYTES = 16 * GS_ROW_BYTES;                // 16 KB, dense [16 rows][1024 B]
 constexpr int GS_ABYTES = GS_KU * 2;                // activation slab (one batch row)
 constexpr int GS_PBYTES = GS_STEPS * 16 * 8;        // (c1, c2) fp32 pairs [step][row]
+constexpr int GS_SBYTES = GS_STEPS * 8;             // (SM, S) fp32 pairs [step]
+constexpr int GS_RAWBYTES = 1024;                   // raw scales [16 rows][16 groups] fp16 + raw zeros (fp16 [16][16] or packed [16 groups][8 B])
 constexpr int GS_STAGE_BYTES = GS_WBYTES + GS_ABYTES + GS_PBYTES;
 constexpr int GS_RED_BYTES = 2 * (2 * GS_NCONS) * 16 * 4;   // two buffers x (8 warps x 2 k-halves) partials x 16 rows
 constexpr int GS_MAX_STAGES = 6;
@@ -81,6 +83,8 @@ struct SlabParams {
   const uint8_t* W;
   unsigned long long* ws;   // [grid][16] tagged partial slots, zero-tagged on entry and on exit
   unsigned int nonce;
+  int dbg;          // tuning diagnostics (BB_GS_DBG): 1 = consumers skip the arithmetic, 4 = no sums prologue, 16 = finisher skips the parameter
+                    // conversion (results are wrong with any of them set)
   int fast_params;  // group size 128, 8-aligned group count, aligned pointers: vector loads of the group parameters
 };
 
@@ -128,16 +132,28 @@ __device__ __forceinline__ float2 gs_lds64f(uint32_t addr) {
   asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void gs_sts64f(uint32_t addr, float a, float b) {
-  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void gs_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void gs_sts64u(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+__device__ __forceinline__ void gs_cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+// the mbarrier receives one arrival from this thread when all its cp.async issued so far have landed
+__device__ __forceinline__ void gs_cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t gs_lds8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ uint32_t gs_lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void gs_sts64f(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ void gs_sts32f(uint32_t addr, float a) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
 __device__ __forceinline__ float gs_lds32f(uint32_t addr) {
@@ -200,16 +216,18 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   const uint32_t Ab = Wb + uint32_t(S) * GS_WBYTES;
   const uint32_t Pb = Ab + uint32_t(S) * GS_ABYTES;
   const uint32_t Rb = Pb + uint32_t(S) * GS_PBYTES;
-  const uint32_t Bb = Rb + GS_RED_BYTES;               // full[S], empty[S]
-  const uint32_t SCRb = Bb + 16u * uint32_t(GS_MAX_STAGES);   // 128 B: the converter's quantized-zeros transpose scratch
-  const uint32_t SUMb = SCRb + 128u;                          // (SM, S) fp32 pairs for every 128-k step of K
+  const uint32_t Bb = Rb + GS_RED_BYTES;               // full[S], afull[S], praw[S], empty[S]
+  const uint32_t Sb = Bb + 32u * uint32_t(GS_MAX_STAGES);     // (SM, S) fp32 pairs [stage][step]
+  const uint32_t RAWb = Sb + uint32_t(GS_MAX_STAGES) * GS_SBYTES;   // raw group parameters [stage]: 512 B scales + 512 B zeros
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      gs_mbar_init(Bb + 8u * s, 2);             // full: loader (arrive.expect_tx of the copies) + converter (parameters written)
-      gs_mbar_init(Bb + 8u * (S + s), GS_NCONS);
+      gs_mbar_init(Bb + 8u * s, 2);             // full: issuer (weights requested, transaction bytes) + finisher (sums + parameters written)
+      gs_mbar_init(Bb + 8u * (S + s), 1);       // afull: activation slab landed
+      gs_mbar_init(Bb + 8u * (2 * S + s), 32);  // praw: the 32 issuer lanes' parameter copies landed
+      gs_mbar_init(Bb + 8u * (3 * S + s), GS_NCONS);   // empty
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -226,169 +244,190 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   const int rb0 = t0 / UPR, ku0 = t0 - rb0 * UPR;
   const int npre = min(S, n_units);
 
-  // weights of one unit: ONE TMA request, box {256 x u32 = 1 KB, 16 rows} of the [N, K/2] byte matrix -> dense [16][1024 B]
-  // (columns past K/2 in a row block's last unit are zero-filled and never consumed; the transaction count is the full box)
-  auto issue_w = [&](int rb, int ku, int slot) {
-    if (lane == 0) gs_tma_2d(Wb + uint32_t(slot) * GS_WBYTES, &tmW, ku * (GS_ROW_BYTES / 4), rb * 16, Bb + 8u * slot);
+  // ---- the two helper warps --------------------------------------------------------------------------------------------
+  // ISSUER (warp 8): for every unit, as soon as its ring slot is free: ONE weight TMA box {256 x u32 = 1 KB, 16 rows} of the
+  //   [N, K/2] byte matrix -> dense [16][1024 B] (columns past K/2 in a row block's last unit are zero-filled and never
+  //   consumed); the activation slab (bulk copy); and the unit's RAW group parameters by cp.async -- 16 B of scales (and of
+  //   fp16 zeros) per (row, half), 8 B of packed zeros per group -- completion signalled on praw[s].  It never waits for data.
+  // FINISHER (warp 9): when the slab has landed, the activation sums of the unit's 16 steps on the tensor cores (S = sum a[k],
+  //   SM = sum magic(k mod 8) a[k]: A fragment = [ones; decode magic of element k mod 8], B columns = 8 different steps); when the
+  //   raw parameters have landed, their conversion to fp32 (c1, c2) pairs [step][row]; then the second arrival on full[s].
+  // Everything a unit needs is requested at the same moment and rides the same queue: the DRAM system runs saturated, so by
+  // Little's law EVERY request -- also a 1-byte parameter load -- takes (bytes in flight) / bandwidth ~ 3 us to come back.
+  // (Measured, profiles/r2_slab_v4_ablation.txt: parameters fetched with plain loads 1 or 4 units ahead of their conversion
+  // stalled the converting warp on every unit: 17.7 us with, 13.2 us without the loads, at 12288^2 with no arithmetic at all.)
+  auto unit_w = [&](int rb, int ku, int slot) {   // lane 0
+    gs_tma_2d(Wb + uint32_t(slot) * GS_WBYTES, &tmW, ku * (GS_ROW_BYTES / 4), rb * 16, Bb + 8u * slot);
   };
-  if (warp == GS_NCONS) {
-    // weights do not depend on the preceding kernel: request the first ring-full before waiting for it
-    int rbp = rb0, kup = ku0;
-    for (int u = 0; u < npre; ++u) {
-      if (lane == 0) gs_mbar_expect_tx_only(Bb + 8u * u, GS_WBYTES);
-      issue_w(rbp, kup, u);
-      if (++kup == UPR) { kup = 0; ++rbp; }
+  const int prow = lane & 15, phalf = lane >> 4;     // helper-warp lane = (weight row, half of the unit's 16 steps)
+  const uint16_t* scale16 = reinterpret_cast<const uint16_t*>(p.scale);
+  const uint16_t* zeros16 = reinterpret_cast<const uint16_t*>(p.zeros);
+  const uint8_t* zeros8 = reinterpret_cast<const uint8_t*>(p.zeros);
+  auto unit_fast = [&](int ku) { return p.fast_params != 0 && (ku + 1) * GS_STEPS <= steps_total; };
+  auto unit_params = [&](int rb, int ku, int slot) {   // all 32 lanes
+    const uint32_t bar = Bb + 8u * (2 * S + slot);
+    if (unit_fast(ku)) {
+      const uint32_t raw = RAWb + uint32_t(slot) * GS_RAWBYTES;
+      const size_t off = size_t(rb * 16 + prow) * p.G + (ku * GS_STEPS + phalf * 8);   // g = 128: group index = step index
+      if (p.with_scaling) gs_cp_async16(raw + uint32_t(prow * 32 + phalf * 16), scale16 + off);
+      if (p.zmode == 1 || p.zmode == 2) gs_cp_async16(raw + 512u + uint32_t(prow * 32 + phalf * 16), zeros16 + off);
+      else if (p.zmode == 3 && lane < GS_STEPS)
+        gs_cp_async8(raw + 512u + uint32_t(lane) * 8u, zeros8 + size_t(ku * GS_STEPS + lane) * (p.N >> 1) + rb * 8);
+      gs_cp_async_arrive_noinc(bar);
+    } else {
+      gs_mbar_arrive(bar);   // slow path: the finisher loads the parameters itself
     }
-  }
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // activations (and our stores) depend on the preceding kernel
-
-  // ---- activation sums per 128-k step, once per CTA: S = sum a[k], SM = sum magic(k mod 8) a[k] (all threads) ----
-  {
-    const uint4* A4 = reinterpret_cast<const uint4*>(p.A);
-    const int nchunks = p.K >> 3;   // 16-byte chunks of 8 activations = the 8 elements of one packed weight word
-    for (int c = int(threadIdx.x); c < nchunks; c += GS_THREADS) {   // nchunks % 32 == 0: whole warps in or out
-      const uint4 v = __ldg(A4 + c);
-      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-      float e[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        e[2 * i] = gs_raw_to_float<T>(w4[i] & 0xffffu);
-        e[2 * i + 1] = gs_raw_to_float<T>(w4[i] >> 16);
-      }
-      float s_all = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-      float sm;
-      if constexpr (!HI) sm = float(TypeTraits<T>::kMagicVal) * s_all;
-      else {
-        // elements decoded from odd nibble positions carry the magic 64 instead of 1024
-        const float s_hi = IL ? ((e[2] + e[3]) + (e[6] + e[7])) : ((e[1] + e[3]) + (e[5] + e[7]));
-        sm = 1024.f * (s_all - s_hi) + 64.f * s_hi;
-      }
-#pragma unroll
-      for (int o = 1; o < 16; o <<= 1) {
-        s_all += __shfl_xor_sync(0xffffffffu, s_all, o);
-        sm += __shfl_xor_sync(0xffffffffu, sm, o);
-      }
-      if ((lane & 15) == 0) gs_sts64f(SUMb + uint32_t(c >> 4) * 8u, sm, s_all);
-    }
-  }
-  __syncthreads();
+  };
 
   if (warp == GS_NCONS) {
-    // =========================== loader warp: one unit = one weight TMA box + the activation slab copy ===========================
+    // =========================== issuer warp ===========================
+    // weights and group parameters do not depend on the preceding kernel: request the first ring-full before waiting for it
+    {
+      int rbp = rb0, kup = ku0;
+      for (int u = 0; u < npre; ++u) {
+        if (lane == 0) { gs_mbar_expect_tx_only(Bb + 8u * u, GS_WBYTES); unit_w(rbp, kup, u); }
+        unit_params(rbp, kup, u);
+        if (++kup == UPR) { kup = 0; ++rbp; }
+      }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the activations depend on the preceding kernel
     int slot = 0, rb = rb0, ku = ku0;
     uint32_t ephase = 1u;   // parity trick: the first pass over the ring finds every slot free
 #pragma unroll 1
     for (int i = 0; i < n_units; ++i) {
-      gs_mbar_wait(Bb + 8u * (S + slot), ephase);
+      gs_mbar_wait(Bb + 8u * (3 * S + slot), ephase);
       const int k0 = ku * GS_KU;
       const uint32_t abytes = uint32_t(min(GS_KU, p.K - k0)) * 2u;
       if (lane == 0) {
-        gs_mbar_expect_tx(Bb + 8u * slot, abytes + (i >= npre ? uint32_t(GS_WBYTES) : 0u));
-        if (i >= npre) issue_w(rb, ku, slot);
-        gs_bulk_g2s(Ab + uint32_t(slot) * GS_ABYTES, reinterpret_cast<const uint8_t*>(p.A) + size_t(k0) * 2, abytes, Bb + 8u * slot);
+        if (i >= npre) {
+          gs_mbar_expect_tx(Bb + 8u * slot, uint32_t(GS_WBYTES));
+          unit_w(rb, ku, slot);
+        } else {
+          gs_mbar_arrive(Bb + 8u * slot);   // (its transaction bytes were registered with the pre-wait request)
+        }
+        gs_mbar_expect_tx(Bb + 8u * (S + slot), abytes);
+        gs_bulk_g2s(Ab + uint32_t(slot) * GS_ABYTES, reinterpret_cast<const uint8_t*>(p.A) + size_t(k0) * 2, abytes, Bb + 8u * (S + slot));
       }
+      if (i >= npre) unit_params(rb, ku, slot);
       if (++slot == S) { slot = 0; ephase ^= 1u; }
       if (++ku == UPR) { ku = 0; ++rb; }
     }
     return;
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // (our stores and workspace traffic must follow the preceding kernel)
 
   if (warp == GS_NCONS + 1) {
-    // =========================== converter warp: scales / zeros of a unit -> fp32 (c1, c2) pairs [step][row] ===========================
-    // lane = (row, half of the unit's 16 steps).  Raw values are loaded one unit ahead (the loop is unrolled by two so that no
-    // register copy ever waits for the loads just issued) and converted when the ring slot is free.  This warp is on the
-    // critical path of every unit (profiles/r2_slab_v2_*: ~490 instructions per unit capped a CTA at one unit per 4200 cycles),
-    // hence the fast path: group size 128 -> the lane's 8 scales (and fp16 zeros) are ONE aligned 16-byte load, the unit's
-    // packed quantized zeros are one 8-byte load per group by lanes 0..15, transposed through 128 bytes of shared memory.
-    const int prow = lane & 15, phalf = lane >> 4;
-    const uint16_t* scale16 = reinterpret_cast<const uint16_t*>(p.scale);
-    const uint16_t* zeros16 = reinterpret_cast<const uint16_t*>(p.zeros);
-    const uint8_t* zeros8 = reinterpret_cast<const uint8_t*>(p.zeros);
-    const uint32_t scratch = SCRb;
+    // =========================== finisher warp ===========================
+    const int g8 = lane >> 2, t4 = lane & 3;
+    uint32_t sfrag[4] = {0u, 0u, 0u, 0u};
+    {
+      const uint32_t one2 = F16 ? 0x3c003c00u : 0x3f803f80u;
+      uint32_t pat;
+      if (!HI) pat = MAGIC;                                   // (magic, magic)
+      else if (IL) pat = (t4 & 1) ? MAGIC_HI : MAGIC;          // elements {2,3,6,7} of a word sit in odd nibbles
+      else pat = 0x54006400u;                                  // (even element: 1024, odd element: 64)
+      if (g8 == 0) { sfrag[0] = one2; sfrag[2] = one2; }
+      if (g8 == 1) { sfrag[0] = pat; sfrag[2] = pat; }
+    }
     const uint32_t zsh = 4u * uint32_t(prow & 1);
-    uint4 sA = make_uint4(0u, 0u, 0u, 0u), zA = sA, sB = sA, zB = sA;
-    bool fA = false, fB = false;
     int slot = 0, rb = rb0, ku = ku0;
-    uint32_t ephase = 1u;
-    // raw parameters of unit (rb, ku) as 8 x 16-bit per lane (s4: scales; z4: fp16 zeros, or -- quantized -- the raw byte holding
-    // this row's zero point, or on the fast path the whole group's 8 packed bytes in lanes 0..15); advances (rb, ku)
-    auto fetch = [&](uint4& s4, uint4& z4, bool& fastu) {
-      const int n = rb * 16 + prow;
-      const int kstep = ku * GS_STEPS + phalf * 8;
-      fastu = p.fast_params != 0 && (ku + 1) * GS_STEPS <= steps_total;
-      if (fastu) {
-        const size_t off = size_t(n) * p.G + kstep;   // g = 128: group index = step index
-        if (p.with_scaling) s4 = __ldg(reinterpret_cast<const uint4*>(scale16 + off));
-        if (p.zmode == 1 || p.zmode == 2) z4 = __ldg(reinterpret_cast<const uint4*>(zeros16 + off));
-        else if (p.zmode == 3 && lane < 16) {
-          const uint2 v = __ldg(reinterpret_cast<const uint2*>(zeros8 + size_t(ku * GS_STEPS + lane) * (p.N >> 1) + rb * 8));
-          z4.x = v.x; z4.y = v.y;
-        }
-      } else {
-        int gi = kstep / p.g128, rem = kstep - gi * p.g128;
-        uint32_t sc[8], zc[8];
+    uint32_t phase = 0u;
+#pragma unroll 1
+    for (int i = 0; i < n_units; ++i) {
+      // ---- activation sums of the unit's 16 steps ----
+      gs_mbar_wait(Bb + 8u * (S + slot), phase);
+      if (!(p.dbg & 4)) {
+        const uint32_t abase = Ab + uint32_t(slot) * GS_ABYTES;
+        const uint32_t sbase = Sb + uint32_t(slot) * GS_SBYTES;
+        // column g8 of the B operand = step 8 h + g8; its 16-k blocks are visited in an order rotated by g8 (bank spread) -- any
+        // order is fine as long as (physical k) = (MMA k slot) mod 8, which the magic-pattern row relies on.  All B fragments are
+        // loaded first and the 16 MMAs run as four independent chains.
+        uint32_t bf[2][8][2];
 #pragma unroll
-        for (int st = 0; st < 8; ++st) {
-          sc[st] = 0u; zc[st] = 0u;
-          if (kstep + st < steps_total) {
-            if (p.with_scaling) sc[st] = __ldg(scale16 + size_t(n) * p.G + gi);
-            if (p.zmode == 1 || p.zmode == 2) zc[st] = __ldg(zeros16 + size_t(n) * p.G + gi);
-            else if (p.zmode == 3) zc[st] = __ldg(zeros8 + size_t(gi) * (p.N >> 1) + (n >> 1));
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int ms = 0; ms < 8; ++ms) {
+            const uint32_t a = abase + uint32_t((8 * h + g8) * 128 + ((ms + g8) & 7) * 16 + 2 * t4) * 2u;
+            bf[h][ms][0] = gs_lds32(a);
+            bf[h][ms][1] = gs_lds32(a + 16u);
           }
-          if (++rem == p.g128) { rem = 0; ++gi; }
-        }
-        s4 = make_uint4(sc[0] | (sc[1] << 16), sc[2] | (sc[3] << 16), sc[4] | (sc[5] << 16), sc[6] | (sc[7] << 16));
-        z4 = make_uint4(zc[0] | (zc[1] << 16), zc[2] | (zc[3] << 16), zc[4] | (zc[5] << 16), zc[6] | (zc[7] << 16));
-      }
-      if (++ku == UPR) { ku = 0; ++rb; }
-    };
-    auto convert = [&](const uint4& s4, const uint4& z4, bool fastu) {
-      gs_mbar_wait(Bb + 8u * (S + slot), ephase);
-      const bool zq_fast = fastu && p.zmode == 3;
-      if (zq_fast) {
-        if (lane < 16) gs_sts64u(scratch + uint32_t(lane) * 8u, z4.x, z4.y);
-        __syncwarp();
-      }
-      const uint32_t pbase = Pb + uint32_t(slot) * GS_PBYTES + uint32_t(phalf * 8 * 16 + prow) * 8u;
-      const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w}, zw[4] = {z4.x, z4.y, z4.z, z4.w};
-      // the zero-point mode is hoisted out of the per-step loop (a switch inside it compiles to eight indirect branches)
-      auto body = [&](auto zm_tag, auto sc_tag) {
-        constexpr int ZM = decltype(zm_tag)::value;
-        constexpr bool SC = decltype(sc_tag)::value;
 #pragma unroll
-        for (int st = 0; st < 8; ++st) {
-          const uint32_t sraw = (st & 1) ? (sw[st >> 1] >> 16) : (sw[st >> 1] & 0xffffu);
-          const uint32_t zraw = (st & 1) ? (zw[st >> 1] >> 16) : (zw[st >> 1] & 0xffffu);
-          const float c1 = SC ? gs_raw_to_float<T>(sraw) : 1.f;
-          float c2;
-          if constexpr (ZM == 0) c2 = -c1 * float(p.zp_const);
-          else if constexpr (ZM == 1) c2 = -c1 * gs_raw_to_float<T>(zraw);
-          else if constexpr (ZM == 2) c2 = -gs_raw_to_float<T>(zraw);
-          else if constexpr (ZM == 3) c2 = -c1 * float((zraw >> zsh) & 15u);
-          else c2 = -c1 * float((gs_lds8(scratch + uint32_t(phalf * 8 + st) * 8u + uint32_t(prow >> 1)) >> zsh) & 15u);
-          gs_sts64f(pbase + uint32_t(st) * 128u, c1, c2);
+        for (int h = 0; h < 2; ++h) {
+          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ms = 0; ms < 4; ++ms) {
+            gs_mma<T>(c0, sfrag, bf[h][ms][0], bf[h][ms][1]);
+            gs_mma<T>(c1, sfrag, bf[h][ms + 4][0], bf[h][ms + 4][1]);
+          }
+          if (g8 < 2) {   // row 0: S -> .y, row 1: SM -> .x
+            const uint32_t d = sbase + uint32_t(8 * h + 2 * t4) * 8u + (g8 == 0 ? 4u : 0u);
+            gs_sts32f(d, c0[0] + c1[0]);
+            gs_sts32f(d + 8u, c0[1] + c1[1]);
+          }
         }
-      };
-      using std::integral_constant;
-      if (zq_fast) body(integral_constant<int, 4>{}, std::true_type{});
-      else if (!p.with_scaling) body(integral_constant<int, 0>{}, std::false_type{});   // (zeros need scaling: gemv_slab_supported)
-      else if (p.zmode == 0) body(integral_constant<int, 0>{}, std::true_type{});
-      else if (p.zmode == 1) body(integral_constant<int, 1>{}, std::true_type{});
-      else if (p.zmode == 2) body(integral_constant<int, 2>{}, std::true_type{});
-      else body(integral_constant<int, 3>{}, std::true_type{});
+      }
+      // ---- group parameters -> fp32 (c1, c2) pairs ----
+      gs_mbar_wait(Bb + 8u * (2 * S + slot), phase);
+      if (!(p.dbg & 16)) {
+        uint32_t sc[8], zc[8];   // raw 16-bit scales; raw fp16 zeros or (quantized) the byte holding this row's zero point
+        if (unit_fast(ku)) {
+          const uint32_t raw = RAWb + uint32_t(slot) * GS_RAWBYTES;
+          const uint4 s4 = gs_lds128(raw + uint32_t(prow * 32 + phalf * 16));
+          const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int st = 0; st < 8; ++st) sc[st] = (st & 1) ? (sw[st >> 1] >> 16) : (sw[st >> 1] & 0xffffu);
+          if (p.zmode == 3) {
+#pragma unroll
+            for (int st = 0; st < 8; ++st) zc[st] = gs_lds8(raw + 512u + uint32_t(phalf * 8 + st) * 8u + uint32_t(prow >> 1));
+          } else {
+            const uint4 z4 = gs_lds128(raw + 512u + uint32_t(prow * 32 + phalf * 16));
+            const uint32_t zw[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+            for (int st = 0; st < 8; ++st) zc[st] = (st & 1) ? (zw[st >> 1] >> 16) : (zw[st >> 1] & 0xffffu);
+          }
+        } else {
+          // slow path (group size != 128, unaligned parameter tensors, a row block's ragged last unit): synchronous loads
+          const int n = rb * 16 + prow;
+          const int kstep = ku * GS_STEPS + phalf * 8;
+          int gi = kstep / p.g128, rem = kstep - gi * p.g128;
+#pragma unroll
+          for (int st = 0; st < 8; ++st) {
+            sc[st] = 0u; zc[st] = 0u;
+            if (kstep + st < steps_total) {
+              if (p.with_scaling) sc[st] = __ldg(scale16 + size_t(n) * p.G + gi);
+              if (p.zmode == 1 || p.zmode == 2) zc[st] = __ldg(zeros16 + size_t(n) * p.G + gi);
+              else if (p.zmode == 3) zc[st] = __ldg(zeros8 + size_t(gi) * (p.N >> 1) + (n >> 1));
+            }
+            if (++rem == p.g128) { rem = 0; ++gi; }
+          }
+        }
+        const uint32_t pbase = Pb + uint32_t(slot) * GS_PBYTES + uint32_t(phalf * 8 * 16 + prow) * 8u;
+        // the zero-point mode is hoisted out of the per-step loop (a switch inside it compiles to eight indirect branches)
+        auto body = [&](auto zm_tag, auto sc_tag) {
+          constexpr int ZM = decltype(zm_tag)::value;
+          constexpr bool SC = decltype(sc_tag)::value;
+#pragma unroll
+          for (int st = 0; st < 8; ++st) {
+            const float c1 = SC ? gs_raw_to_float<T>(sc[st]) : 1.f;
+            float c2;
+            if constexpr (ZM == 0) c2 = -c1 * float(p.zp_const);
+            else if constexpr (ZM == 1) c2 = -c1 * gs_raw_to_float<T>(zc[st]);
+            else if constexpr (ZM == 2) c2 = -gs_raw_to_float<T>(zc[st]);
+            else c2 = -c1 * float((zc[st] >> zsh) & 15u);
+            gs_sts64f(pbase + uint32_t(st) * 128u, c1, c2);
+          }
+        };
+        using std::integral_constant;
+        if (!p.with_scaling) body(integral_constant<int, 0>{}, std::false_type{});   // (zeros need scaling: gemv_slab_supported)
+        else if (p.zmode == 0) body(integral_constant<int, 0>{}, std::true_type{});
+        else if (p.zmode == 1) body(integral_constant<int, 1>{}, std::true_type{});
+        else if (p.zmode == 2) body(integral_constant<int, 2>{}, std::true_type{});
+        else body(integral_constant<int, 3>{}, std::true_type{});
+      }
       __syncwarp();
       if (lane == 0) gs_mbar_arrive(Bb + 8u * slot);
-      if (++slot == S) { slot = 0; ephase ^= 1u; }
-    };
-    if (n_units > 0) fetch(sA, zA, fA);
-#pragma unroll 1
-    for (int i = 0; i < n_units; i += 2) {
-      if (i + 1 < n_units) fetch(sB, zB, fB);
-      convert(sA, zA, fA);
-      if (i + 1 < n_units) {
-        if (i + 2 < n_units) fetch(sA, zA, fA);
-        convert(sB, zB, fB);
-      }
+      if (++slot == S) { slot = 0; phase ^= 1u; }
+      if (++ku == UPR) { ku = 0; ++rb; }
     }
     return;
   }
@@ -420,15 +459,15 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   int rb = t0 / UPR, ku = t0 - rb * UPR;
   bool seg_from0 = (ku == 0);
   const int nsl_last = (Kb - (UPR - 1) * (GS_NCONS * GS_SLICE_BYTES)) / GS_SLICE_BYTES;   // valid K-slices of a row block's last unit
-  uint32_t wst = Wb + woff, ast = Ab + aoff, pst = Pb + poff;
-  uint32_t fbar = Bb, ebar = Bb + 8u * uint32_t(S);
+  uint32_t wst = Wb + woff, ast = Ab + aoff, pst = Pb + poff, sst = Sb + soff;
+  uint32_t fbar = Bb, ebar = Bb + 8u * uint32_t(3 * S);
 
 #pragma unroll 1
   for (int t = t0; t < t1; ++t) {
     const bool closes = (ku == UPR - 1);
     gs_mbar_wait(fbar, fphase);
-    if (!closes || w < nsl_last) {
-      const float2 su = gs_lds64f(SUMb + soff + uint32_t(ku) * (GS_STEPS * 8u));
+    if ((!closes || w < nsl_last) && !(p.dbg & 1)) {
+      const float2 su = gs_lds64f(sst);
       uint4 wv[4];
 #pragma unroll
       for (int x = 0; x < 4; ++x) wv[x] = gs_lds128(wst + uint32_t(x) * (4u * GS_ROW_BYTES));
@@ -483,10 +522,10 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
     }
     __syncwarp();
     if (lane == 0) gs_mbar_arrive(ebar);
-    wst += GS_WBYTES; ast += GS_ABYTES; pst += GS_PBYTES; fbar += 8u; ebar += 8u;
+    wst += GS_WBYTES; ast += GS_ABYTES; pst += GS_PBYTES; sst += GS_SBYTES; fbar += 8u; ebar += 8u;
     if (++slot == S) {
       slot = 0; fphase ^= 1u;
-      wst = Wb + woff; ast = Ab + aoff; pst = Pb + poff; fbar = Bb; ebar = Bb + 8u * uint32_t(S);
+      wst = Wb + woff; ast = Ab + aoff; pst = Pb + poff; sst = Sb + soff; fbar = Bb; ebar = Bb + 8u * uint32_t(3 * S);
     }
 
     if (closes || t == t1 - 1) {
@@ -589,7 +628,7 @@ bool get_w_map(CUtensorMap* tm, const void* W, int N, int K) {
   return true;
 }
 
-int gs_smem_bytes(int stages, int K) { return 1024 + stages * GS_STAGE_BYTES + GS_RED_BYTES + 16 * GS_MAX_STAGES + 128 + (K / 128) * 8 + 64; }
+int gs_smem_bytes(int stages, int /*K*/) { return 1024 + stages * GS_STAGE_BYTES + GS_RED_BYTES + GS_MAX_STAGES * (32 + GS_SBYTES + GS_RAWBYTES) + 64; }
 
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -672,6 +711,7 @@ int launch_gemv_slab(const MatmulArgs& a) {
   stages = std::max(2, std::min(GS_MAX_STAGES, stages));
   p.stages = stages;
   p.W = reinterpret_cast<const uint8_t*>(a.W);
+  p.dbg = env_int("BB_GS_DBG", 0);
   CUtensorMap tm;
   if (!get_w_map(&tm, a.W, d.N, d.K)) { set_error("gemv_slab: cuTensorMapEncodeTiled failed"); return 4; }
   p.fast_params = (p.g128 == 1 && (p.G & 7) == 0 && (!d.with_scaling || (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0) &&
