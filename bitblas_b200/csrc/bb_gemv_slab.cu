@@ -2,38 +2,39 @@
 //
 // Replaces the reference's generated SIMT GEMV (bitblas/ops/general_matmul/tilelang/dequantize/gemv_dequantize_simt.py:164-262)
 // and supersedes the round-1 register-queue kernel (bb_gemv.cu: 0.40 of the HBM roofline, bound by instruction issue and by
-// DRAM round trips sitting on the warps' scoreboards).  Design, top down:
+// DRAM round trips sitting on the warps' scoreboards).  Design, top down (every choice below was measured on B200; the
+// intermediate versions and their ablations are in profiles/r2_slab_v*.txt):
 //
-//   * WORK UNIT = [16 weight rows] x [2048 k] = 16 KB of packed weights out of the unchanged [N, K/2] storage, fetched by ONE TMA
-//     request: box {256 x u32 = 1 KB, 16 rows}, no swizzle -- a DRAM page activation serves 1 KB instead of 64-128 B.  Measured
-//     on B200 (profiles/r2_slabbench.txt, r2_slab_v0_bench.txt, r2_slab_v1_bulk1d_bench.txt), two issuing CTAs per SM, 12288^2:
-//     this box streams at the linear-read rate (5.2 TB/s with ~4 us of launch gaps); the 128B-swizzled layout a GEMM would use
-//     ({128 B, 16 rows, 8 slices} per request) only 1.2-1.6 TB/s; sixteen 1 KB cp.async.bulk copies per unit 2.1 TB/s -- the TMA
-//     engine pays per request and per box row, so rows must be long and requests few.  The dense [16][1024 B] landing zone is
-//     read conflict-free through the two-column fragment mapping described at the consumer loop.  Units are ordered row block by row block and cut into equal
-//     contiguous ranges over a persistent grid (CTA-level stream-K): every SM streams the same number of bytes whatever N, K
-//     are; a 1024-row tensor-parallel shard still fills all 148 SMs.
-//   * a CTA = 8 consumer warps + a loader warp + a parameter-converter warp around an S-stage mbarrier ring in shared memory.  The consumers issue NO
-//     global loads: weights, activations, group parameters and activation group sums are all in the stage when its barrier
-//     flips, so nothing but ld.shared latency ever sits on a consumer scoreboard.
-//   * consumer warp w owns K-slice w of the unit (16 rows x 128 B = two 128-k steps): ld.shared.v4 -> LOP3 decode into
-//     mma.sync.m16n8k16 A fragments (fp16: even nibbles as 1024+u, odd nibbles in place as 64+u) -> 8 HMMA per step with the
-//     activations as the n8 side.  The decode magic and the zero point are never subtracted per element and never folded
-//     through extra MMAs (round 1 spent half its HMMAs on that): per step
+//   * WORK UNIT = [32 weight rows] x [1024 k] = 16 KB of packed weights out of the unchanged [N, K/2] storage, fetched by ONE TMA
+//     request: box {128 x u32 = 512 B, 32 rows}, no swizzle.  The TMA engine pays per request and per box row: a GEMM-style
+//     128B-swizzled box ({128 B, 16 rows, 8 slices}) streamed DRAM at 1.2-1.6 TB/s, sixteen 1 KB cp.async.bulk copies per unit
+//     at 2.1 TB/s, boxes with long rows at the linear-read rate (tools/slabbench.cu); bandwidth then depends only on the bytes
+//     in flight.  Units are ordered (row-block group, k, member) and cut into equal contiguous ranges over a persistent grid
+//     (CTA-level stream-K): every SM streams the same number of bytes whatever N, K are; a 1024-row tensor-parallel shard
+//     still fills all 148 SMs.
+//   * a CTA = NG consumer GROUPS of 4 warps + an issuer warp + NF finisher warps around an S-stage mbarrier ring.  Group g
+//     consumes the units whose row block is g (mod NG) -- whole row blocks per group, so a group reduces, exchanges stream-K
+//     partials and stores on its own, with a 128-thread named barrier; nothing ever synchronises the whole CTA.  The
+//     consumers issue NO global loads: weights, activations, group parameters and activation sums are all in the stage when its
+//     barrier flips, so nothing but ld.shared latency ever sits on a consumer scoreboard.
+//   * consumer warp ws of a group owns K-slice ws of the unit (32 rows x 128 B = two 128-k steps): ld.shared.v4 -> LOP3 decode
+//     into mma.sync.m16n8k16 A fragments (fp16: even nibbles as 1024+u, odd nibbles in place as 64+u) -> 8 HMMA per step and
+//     16-row tile, the activations as the n8 side and shared by the warp's two row tiles.  The decode magic and the zero point
+//     are never subtracted per element and never folded through extra MMAs (round 1 spent half its HMMAs on that): per step
 //         acc += c1[row] * (partial - SM) + c2[row] * S,    SM = sum_k magic(k) a[k],  S = sum_k a[k]   (per 128-k step)
 //     with (c1, c2) = (s, -s*z) for "original" / quantized zeros, (s, -z) for "rescale", (s, -s*2^(b-1)) for int formats.
 //     This is exact in fp32 for ANY zero point (no integer / fraction split) and is three FMAs per output row per step.
-//   * the loader warp issues the unit's 16 weight-row copies + the activation slab copy; the converter warp fetches the unit's
-//     scales / zeros with plain loads one unit ahead and writes them as fp32 (c1, c2) pairs; (SM, S) for every 128-k step of K
-//     are computed once per CTA by all threads before the stream starts (while the first ring-full of weights is in flight).
-//     (First version, profiles/r2_slab_v0_*: ONE producer warp doing all of that per unit -- ~900 instructions -- capped a
-//     CTA at one unit per ~6000 cycles, 1.6 TB/s chip-wide whatever the ring depth.)
-//   * stream-K fix-up: a range that starts inside a row block parks its CTA-reduced partial row sums in tagged 64-bit
+//   * the ISSUER requests, the moment a ring slot is free, everything the unit needs: the weight box, the activation slab
+//     (bulk copy) and the RAW group parameters (cp.async, 16 B per row); a FINISHER turns the slab into (SM, S) per step on the
+//     tensor cores and the raw parameters into fp32 (c1, c2) pairs, then completes the stage barrier.  The DRAM system runs
+//     saturated, so by Little's law EVERY request -- also a 1-byte parameter load -- takes (bytes in flight)/bandwidth ~ 3 us:
+//     anything fetched with plain loads "a few units ahead" stalls its warp on every unit (measured: 17.7 vs 13.2 us).
+//   * stream-K fix-up: a range that starts inside a row block parks its group-reduced partial row sums in tagged 64-bit
 //     workspace slots {call nonce, fp32}; the range holding the block's first unit adds them in fixed order (bit-reproducible)
 //     and stores.  Ranges are handed out in reverse CTA order so an owner only waits for CTAs dispatched before it.
-//   * programmatic dependent launch: weights of the first S units are requested before griddepcontrol.wait, activations
-//     after it; launch_dependents is raised at kernel entry -- the grid is persistent and fully resident, so the next
-//     kernel's CTAs can only take slots that this kernel's CTAs have vacated, and its weight prefetch overlaps our tail.
+//   * programmatic dependent launch: weights and parameters of the first S units are requested before griddepcontrol.wait,
+//     activations after it; launch_dependents is raised at kernel entry -- the grid is persistent and fully resident, so the
+//     next kernel's CTAs can only take slots that this kernel's CTAs have vacated, and its prefetch overlaps our tail.
 #include <cuda.h>
 
 #include <atomic>
@@ -48,21 +49,21 @@ namespace bb {
 
 namespace {
 
-constexpr int GS_NCONS = 8;                         // consumer warps per CTA = K-slices per unit
-constexpr int GS_THREADS = (GS_NCONS + 2) * 32;     // + loader warp + parameter converter warp
-constexpr int GS_SLICE_BYTES = 128;                 // packed bytes per row per consumer per unit
-constexpr int GS_KU = GS_NCONS * GS_SLICE_BYTES * 2;   // k per unit (4-bit): 2048
-constexpr int GS_STEPS = GS_KU / 128;               // 128-k steps per unit: 16
-constexpr int GS_ROW_BYTES = GS_SLICE_BYTES * GS_NCONS;     // packed bytes per row per unit: 1 KB = one box row of the TMA request
-constexpr int GS_WBYTES = 16 * GS_ROW_BYTES;                // 16 KB, dense [16 rows][1024 B]
-constexpr int GS_ABYTES = GS_KU * 2;                // activation slab (one batch row)
-constexpr int GS_PBYTES = GS_STEPS * 16 * 8;        // (c1, c2) fp32 pairs [step][row]
+constexpr int GS_ROWS = 32;                         // weight rows per unit (two 16-row MMA tiles)
+constexpr int GS_GW = 4;                            // consumer warps per group = K-slices per unit
+constexpr int GS_SLICE_BYTES = 128;                 // packed bytes per row per consumer warp per unit
+constexpr int GS_ROW_BYTES = GS_GW * GS_SLICE_BYTES;   // packed bytes per row per unit: 512 B = one box row of the TMA request
+constexpr int GS_KU = GS_ROW_BYTES * 2;             // k per unit (4-bit): 1024
+constexpr int GS_STEPS = GS_KU / 128;               // 128-k steps per unit: 8
+constexpr int GS_WBYTES = GS_ROWS * GS_ROW_BYTES;   // 16 KB, dense [32 rows][512 B]
+constexpr int GS_ABYTES = GS_KU * 2;                // activation slab (one batch row): 2 KB
+constexpr int GS_PBYTES = GS_STEPS * GS_ROWS * 8;   // (c1, c2) fp32 pairs [step][row]: 2 KB
 constexpr int GS_SBYTES = GS_STEPS * 8;             // (SM, S) fp32 pairs [step]
-constexpr int GS_RAWBYTES = 1024;                   // raw scales [16 rows][16 groups] fp16 + raw zeros (fp16 [16][16] or packed [16 groups][8 B])
-constexpr int GS_STAGE_BYTES = GS_WBYTES + GS_ABYTES + GS_PBYTES;
-constexpr int GS_RED_BYTES = 2 * (2 * GS_NCONS) * 16 * 4;   // two buffers x (8 warps x 2 k-halves) partials x 16 rows
-constexpr int GS_MAX_STAGES = 6;
-constexpr int GS_MAX_CPS = 3;
+constexpr int GS_RAWBYTES = 1024;                   // raw scales [32 rows][8 groups] fp16 + raw zeros (fp16 [32][8] or packed [8 groups][16 B])
+constexpr int GS_RED_GROUP_BYTES = 2 * (2 * GS_GW) * GS_ROWS * 4;   // per group: two buffers x (4 warps x 2 k-halves) partials x 32 rows
+constexpr int GS_MAX_STAGES = 10;
+
+__host__ __device__ constexpr int gs_threads(int NG) { return (GS_GW * NG + 1 + NG / 2) * 32; }
 
 struct SlabParams {
   const void* A;
@@ -77,15 +78,15 @@ struct SlabParams {
   int zmode;        // 0 none, 1 original, 2 rescale, 3 quantized
   int zp_const;
   int out_dtype;
-  int UPR;          // units per 16-row block
-  int T;            // units in total
+  int UPR;          // units per 32-row block = ceil(K / 1024)
+  int NRB;          // 32-row blocks = ceil(N / 32)
+  int T;            // units in total, padded to whole row-block groups
   int stages;
-  const uint8_t* W;
-  unsigned long long* ws;   // [grid][16] tagged partial slots, zero-tagged on entry and on exit
+  unsigned long long* ws;   // [grid][NG][32] tagged partial slots, zero-tagged on entry and on exit
   unsigned int nonce;
-  int dbg;          // tuning diagnostics (BB_GS_DBG): 1 = consumers skip the arithmetic, 4 = no sums prologue, 16 = finisher skips the parameter
-                    // conversion (results are wrong with any of them set)
-  int fast_params;  // group size 128, 8-aligned group count, aligned pointers: vector loads of the group parameters
+  int dbg;          // tuning diagnostics (BB_GS_DBG): 1 = consumers skip the arithmetic, 4 = no sums, 16 = no parameter conversion
+                    // (results are wrong with any of them set)
+  int fast_params;  // group size 128, 8-aligned group count, N % 32 == 0, aligned pointers: 16-byte async copies of the parameters
 };
 
 __device__ __forceinline__ uint32_t gs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -134,9 +135,6 @@ __device__ __forceinline__ float2 gs_lds64f(uint32_t addr) {
 }
 __device__ __forceinline__ void gs_cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void gs_cp_async8(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 // the mbarrier receives one arrival from this thread when all its cp.async issued so far have landed
 __device__ __forceinline__ void gs_cp_async_arrive_noinc(uint32_t bar) {
@@ -202,32 +200,36 @@ __device__ __forceinline__ void gs_store(const SlabParams& p, int n, float v) {
 
 __device__ __forceinline__ int gs_range_begin(int ri, int T, int R) { return int((long long)ri * T / R); }
 
-template <typename T, bool IL, int CPS>
-__global__ void __launch_bounds__(GS_THREADS, CPS)
+
+// NG consumer groups per CTA, MINB CTAs per SM: (2, 2) or (4, 1)
+template <typename T, bool IL, int NG, int MINB>
+__global__ void __launch_bounds__(gs_threads(NG), MINB)
 gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   constexpr bool F16 = std::is_same<T, __half>::value;
   constexpr bool HI = F16;   // odd nibbles decoded in place (mantissa bits 4..7 under exponent 2^6: exactly 64 + u)
   constexpr uint32_t MAGIC = TypeTraits<T>::kMagic;
   constexpr uint32_t MAGIC_HI = 0x54005400u;
+  constexpr int NF = NG / 2;                 // finisher warps
+  constexpr int NCW = GS_GW * NG;            // consumer warps
   extern __shared__ uint8_t gs_raw[];
   const int S = p.stages;
   const uint32_t base = (gs_smem_u32(gs_raw) + 1023u) & ~1023u;
-  const uint32_t Wb = base;
-  const uint32_t Ab = Wb + uint32_t(S) * GS_WBYTES;
-  const uint32_t Pb = Ab + uint32_t(S) * GS_ABYTES;
-  const uint32_t Rb = Pb + uint32_t(S) * GS_PBYTES;
-  const uint32_t Bb = Rb + GS_RED_BYTES;               // full[S], afull[S], praw[S], empty[S]
-  const uint32_t Sb = Bb + 32u * uint32_t(GS_MAX_STAGES);     // (SM, S) fp32 pairs [stage][step]
-  const uint32_t RAWb = Sb + uint32_t(GS_MAX_STAGES) * GS_SBYTES;   // raw group parameters [stage]: 512 B scales + 512 B zeros
+  const uint32_t Wb = base;                                   // [S][32 rows][512 B]
+  const uint32_t Ab = Wb + uint32_t(S) * GS_WBYTES;           // [S][1024 halves]
+  const uint32_t Pb = Ab + uint32_t(S) * GS_ABYTES;           // [S][8 steps][32 rows] (c1, c2)
+  const uint32_t RAWb = Pb + uint32_t(S) * GS_PBYTES;         // [S] raw parameters: 512 B scales + 512 B zeros
+  const uint32_t Sb = RAWb + uint32_t(S) * GS_RAWBYTES;       // [S][8 steps] (SM, S)
+  const uint32_t Rb = Sb + uint32_t(S) * GS_SBYTES;           // [NG] group reduction buffers
+  const uint32_t Bb = Rb + uint32_t(NG) * GS_RED_GROUP_BYTES; // wfull[S], pfull[S], praw[S], empty[S]
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      gs_mbar_init(Bb + 8u * s, 2);             // full: issuer (weights requested, transaction bytes) + finisher (sums + parameters written)
-      gs_mbar_init(Bb + 8u * (S + s), 1);       // afull: activation slab landed
+      gs_mbar_init(Bb + 8u * s, 1);             // wfull: the weight box and the activation slab have landed (issuer arrival + transaction bytes)
+      gs_mbar_init(Bb + 8u * (S + s), 1);       // pfull: the finisher has written the unit's sums and (c1, c2) pairs
       gs_mbar_init(Bb + 8u * (2 * S + s), 32);  // praw: the 32 issuer lanes' parameter copies landed
-      gs_mbar_init(Bb + 8u * (3 * S + s), GS_NCONS);   // empty
+      gs_mbar_init(Bb + 8u * (3 * S + s), GS_GW);   // empty: the four warps of the group that consumed the unit
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,83 +243,91 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   const int UPR = p.UPR;
   const int Kb = p.K >> 1;                  // packed bytes per row
   const int steps_total = p.K >> 7;         // 128-k steps per row
-  const int rb0 = t0 / UPR, ku0 = t0 - rb0 * UPR;
   const int npre = min(S, n_units);
-
-  // ---- the two helper warps --------------------------------------------------------------------------------------------
-  // ISSUER (warp 8): for every unit, as soon as its ring slot is free: ONE weight TMA box {256 x u32 = 1 KB, 16 rows} of the
-  //   [N, K/2] byte matrix -> dense [16][1024 B] (columns past K/2 in a row block's last unit are zero-filled and never
-  //   consumed); the activation slab (bulk copy); and the unit's RAW group parameters by cp.async -- 16 B of scales (and of
-  //   fp16 zeros) per (row, half), 8 B of packed zeros per group -- completion signalled on praw[s].  It never waits for data.
-  // FINISHER (warp 9): when the slab has landed, the activation sums of the unit's 16 steps on the tensor cores (S = sum a[k],
-  //   SM = sum magic(k mod 8) a[k]: A fragment = [ones; decode magic of element k mod 8], B columns = 8 different steps); when the
-  //   raw parameters have landed, their conversion to fp32 (c1, c2) pairs [step][row]; then the second arrival on full[s].
-  // Everything a unit needs is requested at the same moment and rides the same queue: the DRAM system runs saturated, so by
-  // Little's law EVERY request -- also a 1-byte parameter load -- takes (bytes in flight) / bandwidth ~ 3 us to come back.
-  // (Measured, profiles/r2_slab_v4_ablation.txt: parameters fetched with plain loads 1 or 4 units ahead of their conversion
-  // stalled the converting warp on every unit: 17.7 us with, 13.2 us without the loads, at 12288^2 with no arithmetic at all.)
-  auto unit_w = [&](int rb, int ku, int slot) {   // lane 0
-    gs_tma_2d(Wb + uint32_t(slot) * GS_WBYTES, &tmW, ku * (GS_ROW_BYTES / 4), rb * 16, Bb + 8u * slot);
+  // unit t -> (row block rb, k index ku): t = (q * UPR + ku) * NG + g, rb = q * NG + g
+  auto unit_of = [&](int t, int& rb, int& ku) {
+    const int g = t % NG, rest = t / NG;
+    const int q = rest / UPR;
+    ku = rest - q * UPR;
+    rb = q * NG + g;
   };
-  const int prow = lane & 15, phalf = lane >> 4;     // helper-warp lane = (weight row, half of the unit's 16 steps)
+
+  // ---- helper warps ----------------------------------------------------------------------------------------------------
   const uint16_t* scale16 = reinterpret_cast<const uint16_t*>(p.scale);
   const uint16_t* zeros16 = reinterpret_cast<const uint16_t*>(p.zeros);
   const uint8_t* zeros8 = reinterpret_cast<const uint8_t*>(p.zeros);
-  auto unit_fast = [&](int ku) { return p.fast_params != 0 && (ku + 1) * GS_STEPS <= steps_total; };
-  auto unit_params = [&](int rb, int ku, int slot) {   // all 32 lanes
-    const uint32_t bar = Bb + 8u * (2 * S + slot);
-    if (unit_fast(ku)) {
-      const uint32_t raw = RAWb + uint32_t(slot) * GS_RAWBYTES;
-      const size_t off = size_t(rb * 16 + prow) * p.G + (ku * GS_STEPS + phalf * 8);   // g = 128: group index = step index
-      if (p.with_scaling) gs_cp_async16(raw + uint32_t(prow * 32 + phalf * 16), scale16 + off);
-      if (p.zmode == 1 || p.zmode == 2) gs_cp_async16(raw + 512u + uint32_t(prow * 32 + phalf * 16), zeros16 + off);
-      else if (p.zmode == 3 && lane < GS_STEPS)
-        gs_cp_async8(raw + 512u + uint32_t(lane) * 8u, zeros8 + size_t(ku * GS_STEPS + lane) * (p.N >> 1) + rb * 8);
-      gs_cp_async_arrive_noinc(bar);
-    } else {
-      gs_mbar_arrive(bar);   // slow path: the finisher loads the parameters itself
-    }
-  };
+  auto unit_fast = [&](int rb, int ku) { return p.fast_params != 0 && (ku + 1) * GS_STEPS <= steps_total && rb < p.NRB; };
 
-  if (warp == GS_NCONS) {
+  if (warp == NCW) {
     // =========================== issuer warp ===========================
+    // one weight TMA box {128 x u32 = 512 B, 32 rows} -> dense [32][512 B] (rows past N / columns past K/2 are zero-filled and
+    // never stored / consumed; the transaction count is always the full box), the activation slab, the raw parameters
+    auto unit_w = [&](int rb, int ku, int slot) {   // lane 0
+      gs_tma_2d(Wb + uint32_t(slot) * GS_WBYTES, &tmW, ku * (GS_ROW_BYTES / 4), rb * GS_ROWS, Bb + 8u * slot);
+    };
+    auto unit_params = [&](int rb, int ku, int slot) {   // all 32 lanes: lane = row of the unit
+      const uint32_t bar = Bb + 8u * (2 * S + slot);
+      if (unit_fast(rb, ku)) {
+        const uint32_t raw = RAWb + uint32_t(slot) * GS_RAWBYTES;
+        const size_t off = size_t(rb * GS_ROWS + lane) * p.G + ku * GS_STEPS;   // g = 128: group index = step index
+        if (p.with_scaling) gs_cp_async16(raw + uint32_t(lane) * 16u, scale16 + off);
+        if (p.zmode == 1 || p.zmode == 2) gs_cp_async16(raw + 512u + uint32_t(lane) * 16u, zeros16 + off);
+        else if (p.zmode == 3 && lane < GS_STEPS)
+          gs_cp_async16(raw + 512u + uint32_t(lane) * 16u, zeros8 + size_t(ku * GS_STEPS + lane) * (p.N >> 1) + rb * (GS_ROWS / 2));
+        gs_cp_async_arrive_noinc(bar);
+      } else {
+        gs_mbar_arrive(bar);   // slow path: the finisher loads the parameters itself
+      }
+    };
     // weights and group parameters do not depend on the preceding kernel: request the first ring-full before waiting for it
+    int q0, ku0, g0;   // the range's first unit
     {
-      int rbp = rb0, kup = ku0;
+      const int rest = t0 / NG;
+      g0 = t0 - rest * NG; q0 = rest / UPR; ku0 = rest - q0 * UPR;
+    }
+    auto next_unit = [&](int& qq, int& kk, int& gg) {   // t -> t + 1 in (q, ku, g) coordinates: no division per unit
+      if (++gg == NG) { gg = 0; if (++kk == UPR) { kk = 0; ++qq; } }
+    };
+    {
+      int qq = q0, kk = ku0, gg = g0;
       for (int u = 0; u < npre; ++u) {
-        if (lane == 0) { gs_mbar_expect_tx_only(Bb + 8u * u, GS_WBYTES); unit_w(rbp, kup, u); }
-        unit_params(rbp, kup, u);
-        if (++kup == UPR) { kup = 0; ++rbp; }
+        const int rb = qq * NG + gg;
+        if (lane == 0 && rb < p.NRB) { gs_mbar_expect_tx_only(Bb + 8u * u, GS_WBYTES); unit_w(rb, kk, u); }
+        unit_params(rb, kk, u);
+        next_unit(qq, kk, gg);
       }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");   // the activations depend on the preceding kernel
-    int slot = 0, rb = rb0, ku = ku0;
+    int slot = 0, qq = q0, ku = ku0, gg = g0;
     uint32_t ephase = 1u;   // parity trick: the first pass over the ring finds every slot free
 #pragma unroll 1
     for (int i = 0; i < n_units; ++i) {
+      const int rb = qq * NG + gg;
       gs_mbar_wait(Bb + 8u * (3 * S + slot), ephase);
       const int k0 = ku * GS_KU;
       const uint32_t abytes = uint32_t(min(GS_KU, p.K - k0)) * 2u;
       if (lane == 0) {
-        if (i >= npre) {
-          gs_mbar_expect_tx(Bb + 8u * slot, uint32_t(GS_WBYTES));
-          unit_w(rb, ku, slot);
-        } else {
-          gs_mbar_arrive(Bb + 8u * slot);   // (its transaction bytes were registered with the pre-wait request)
-        }
-        gs_mbar_expect_tx(Bb + 8u * (S + slot), abytes);
-        gs_bulk_g2s(Ab + uint32_t(slot) * GS_ABYTES, reinterpret_cast<const uint8_t*>(p.A) + size_t(k0) * 2, abytes, Bb + 8u * (S + slot));
+        // (the weight bytes of the first ring-full were registered with the pre-wait request; the padding units past the last
+        //  row block -- they exist when NRB % NG != 0 -- carry no weights)
+        const bool w_now = i >= npre && rb < p.NRB;
+        gs_mbar_expect_tx(Bb + 8u * slot, abytes + (w_now ? uint32_t(GS_WBYTES) : 0u));
+        if (w_now) unit_w(rb, ku, slot);
+        gs_bulk_g2s(Ab + uint32_t(slot) * GS_ABYTES, reinterpret_cast<const uint8_t*>(p.A) + size_t(k0) * 2, abytes, Bb + 8u * slot);
       }
       if (i >= npre) unit_params(rb, ku, slot);
       if (++slot == S) { slot = 0; ephase ^= 1u; }
-      if (++ku == UPR) { ku = 0; ++rb; }
+      next_unit(qq, ku, gg);
     }
     return;
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");   // (our stores and workspace traffic must follow the preceding kernel)
 
-  if (warp == GS_NCONS + 1) {
-    // =========================== finisher warp ===========================
+  if (warp > NCW) {
+    // =========================== finisher warp f: units i = f, f + NF, ... of the range ===========================
+    // when the slab has landed: the activation sums of the unit's 8 steps on the tensor cores (A fragment = [ones; the decode
+    // magic of element k mod 8], B column g8 = step g8); when the raw parameters have landed: fp32 (c1, c2) pairs [step][row]
+    // (lane = row); then the second arrival on full[s]
+    const int f = warp - NCW - 1;
     const int g8 = lane >> 2, t4 = lane & 3;
     uint32_t sfrag[4] = {0u, 0u, 0u, 0u};
     {
@@ -329,71 +339,66 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
       if (g8 == 0) { sfrag[0] = one2; sfrag[2] = one2; }
       if (g8 == 1) { sfrag[0] = pat; sfrag[2] = pat; }
     }
-    const uint32_t zsh = 4u * uint32_t(prow & 1);
-    int slot = 0, rb = rb0, ku = ku0;
+    const uint32_t zsh = 4u * uint32_t(lane & 1);
+    int rb, ku, gg, slot = f;
     uint32_t phase = 0u;
+    unit_of(t0 + f, rb, ku);   // (one division per kernel; the loop advances the coordinates incrementally)
+    gg = (t0 + f) % NG;
 #pragma unroll 1
-    for (int i = 0; i < n_units; ++i) {
-      // ---- activation sums of the unit's 16 steps ----
-      gs_mbar_wait(Bb + 8u * (S + slot), phase);
+    for (int i = f; i < n_units; i += NF) {
+      // ---- activation sums ----
+      gs_mbar_wait(Bb + 8u * slot, phase);
       if (!(p.dbg & 4)) {
         const uint32_t abase = Ab + uint32_t(slot) * GS_ABYTES;
-        const uint32_t sbase = Sb + uint32_t(slot) * GS_SBYTES;
-        // column g8 of the B operand = step 8 h + g8; its 16-k blocks are visited in an order rotated by g8 (bank spread) -- any
-        // order is fine as long as (physical k) = (MMA k slot) mod 8, which the magic-pattern row relies on.  All B fragments are
-        // loaded first and the 16 MMAs run as four independent chains.
-        uint32_t bf[2][8][2];
+        // column g8 of the B operand = step g8; its 16-k blocks are visited in an order rotated by g8 (bank spread) -- any order
+        // is fine as long as (physical k) = (MMA k slot) mod 8, which the magic-pattern row relies on; two independent chains
+        uint32_t bf[8][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int ms = 0; ms < 8; ++ms) {
+          const uint32_t a = abase + uint32_t(g8 * 128 + ((ms + g8) & 7) * 16 + 2 * t4) * 2u;
+          bf[ms][0] = gs_lds32(a);
+          bf[ms][1] = gs_lds32(a + 16u);
+        }
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int ms = 0; ms < 8; ++ms) {
-            const uint32_t a = abase + uint32_t((8 * h + g8) * 128 + ((ms + g8) & 7) * 16 + 2 * t4) * 2u;
-            bf[h][ms][0] = gs_lds32(a);
-            bf[h][ms][1] = gs_lds32(a + 16u);
-          }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int ms = 0; ms < 4; ++ms) {
-            gs_mma<T>(c0, sfrag, bf[h][ms][0], bf[h][ms][1]);
-            gs_mma<T>(c1, sfrag, bf[h][ms + 4][0], bf[h][ms + 4][1]);
-          }
-          if (g8 < 2) {   // row 0: S -> .y, row 1: SM -> .x
-            const uint32_t d = sbase + uint32_t(8 * h + 2 * t4) * 8u + (g8 == 0 ? 4u : 0u);
-            gs_sts32f(d, c0[0] + c1[0]);
-            gs_sts32f(d + 8u, c0[1] + c1[1]);
-          }
+        for (int ms = 0; ms < 4; ++ms) {
+          gs_mma<T>(c0, sfrag, bf[ms][0], bf[ms][1]);
+          gs_mma<T>(c1, sfrag, bf[ms + 4][0], bf[ms + 4][1]);
+        }
+        if (g8 < 2) {   // row 0: S -> .y, row 1: SM -> .x
+          const uint32_t d = Sb + uint32_t(slot) * GS_SBYTES + uint32_t(2 * t4) * 8u + (g8 == 0 ? 4u : 0u);
+          gs_sts32f(d, c0[0] + c1[0]);
+          gs_sts32f(d + 8u, c0[1] + c1[1]);
         }
       }
       // ---- group parameters -> fp32 (c1, c2) pairs ----
       gs_mbar_wait(Bb + 8u * (2 * S + slot), phase);
       if (!(p.dbg & 16)) {
         uint32_t sc[8], zc[8];   // raw 16-bit scales; raw fp16 zeros or (quantized) the byte holding this row's zero point
-        if (unit_fast(ku)) {
+        if (unit_fast(rb, ku)) {
           const uint32_t raw = RAWb + uint32_t(slot) * GS_RAWBYTES;
-          const uint4 s4 = gs_lds128(raw + uint32_t(prow * 32 + phalf * 16));
+          const uint4 s4 = gs_lds128(raw + uint32_t(lane) * 16u);
           const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
           for (int st = 0; st < 8; ++st) sc[st] = (st & 1) ? (sw[st >> 1] >> 16) : (sw[st >> 1] & 0xffffu);
           if (p.zmode == 3) {
 #pragma unroll
-            for (int st = 0; st < 8; ++st) zc[st] = gs_lds8(raw + 512u + uint32_t(phalf * 8 + st) * 8u + uint32_t(prow >> 1));
+            for (int st = 0; st < 8; ++st) zc[st] = gs_lds8(raw + 512u + uint32_t(st) * 16u + uint32_t(lane >> 1));
           } else {
-            const uint4 z4 = gs_lds128(raw + 512u + uint32_t(prow * 32 + phalf * 16));
+            const uint4 z4 = gs_lds128(raw + 512u + uint32_t(lane) * 16u);
             const uint32_t zw[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
             for (int st = 0; st < 8; ++st) zc[st] = (st & 1) ? (zw[st >> 1] >> 16) : (zw[st >> 1] & 0xffffu);
           }
         } else {
-          // slow path (group size != 128, unaligned parameter tensors, a row block's ragged last unit): synchronous loads
-          const int n = rb * 16 + prow;
-          const int kstep = ku * GS_STEPS + phalf * 8;
+          // slow path (group size != 128, unaligned parameter tensors, N % 32 != 0, a row block's ragged last unit): synchronous loads
+          const int n = rb * GS_ROWS + lane;
+          const int kstep = ku * GS_STEPS;
           int gi = kstep / p.g128, rem = kstep - gi * p.g128;
 #pragma unroll
           for (int st = 0; st < 8; ++st) {
             sc[st] = 0u; zc[st] = 0u;
-            if (kstep + st < steps_total) {
+            if (kstep + st < steps_total && n < p.N) {
               if (p.with_scaling) sc[st] = __ldg(scale16 + size_t(n) * p.G + gi);
               if (p.zmode == 1 || p.zmode == 2) zc[st] = __ldg(zeros16 + size_t(n) * p.G + gi);
               else if (p.zmode == 3) zc[st] = __ldg(zeros8 + size_t(gi) * (p.N >> 1) + (n >> 1));
@@ -401,7 +406,7 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
             if (++rem == p.g128) { rem = 0; ++gi; }
           }
         }
-        const uint32_t pbase = Pb + uint32_t(slot) * GS_PBYTES + uint32_t(phalf * 8 * 16 + prow) * 8u;
+        const uint32_t pbase = Pb + uint32_t(slot) * GS_PBYTES + uint32_t(lane) * 8u;
         // the zero-point mode is hoisted out of the per-step loop (a switch inside it compiles to eight indirect branches)
         auto body = [&](auto zm_tag, auto sc_tag) {
           constexpr int ZM = decltype(zm_tag)::value;
@@ -414,7 +419,7 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
             else if constexpr (ZM == 1) c2 = -c1 * gs_raw_to_float<T>(zc[st]);
             else if constexpr (ZM == 2) c2 = -gs_raw_to_float<T>(zc[st]);
             else c2 = -c1 * float((zc[st] >> zsh) & 15u);
-            gs_sts64f(pbase + uint32_t(st) * 128u, c1, c2);
+            gs_sts64f(pbase + uint32_t(st) * (GS_ROWS * 8u), c1, c2);
           }
         };
         using std::integral_constant;
@@ -425,53 +430,64 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
         else body(integral_constant<int, 3>{}, std::true_type{});
       }
       __syncwarp();
-      if (lane == 0) gs_mbar_arrive(Bb + 8u * slot);
-      if (++slot == S) { slot = 0; phase ^= 1u; }
-      if (++ku == UPR) { ku = 0; ++rb; }
+      if (lane == 0) gs_mbar_arrive(Bb + 8u * (S + slot));
+      slot += NF;                       // S % NF == 0: the slot sequence of this warp closes on itself
+      if (slot >= S) { slot -= S; phase ^= 1u; }
+      gg += NF; rb += NF;               // t -> t + NF
+      if (gg >= NG) { gg -= NG; rb -= NG; if (++ku == UPR) { ku = 0; rb += NG; } }
     }
     return;
   }
 
-  // =========================== consumer warps ===========================
-  // The slab is dense ([16 rows][1024 B]): a 128-bit shared load is conflict-free only if the 8 lanes of one phase read 128
+  // =========================== consumer groups ===========================
+  // The slab is dense ([32 rows][512 B]): a 128-bit shared load is conflict-free only if the 8 lanes of one phase read 128
   // contiguous bytes of ONE row.  So lane L = 8 i + c loads chunk c (16 B = 32 k) of this warp's 128-byte slice for rows
-  // i, 4+i, 8+i, 12+i.  In mma.sync terms (row slot r = L >> 2 = 2 i + b, t = L & 3) the slots with b = 0 then hold the
-  // slice's first 128 k (step 2w) and the slots with b = 1 its second 128 k (step 2w+1) OF THE SAME weight rows -- different
-  // k in one MMA.  That is legal here because m = 1 leaves 7 of the 8 B-operand columns free: column 0 carries the activations
-  // of step 2w, column 1 those of step 2w+1; slot r's result is valid in column b only (lane (r, t = 0), register c[b]).
-  const int w = warp;
+  // i, 4+i, ..., 28+i.  In mma.sync terms (row slot r = L >> 2 = 2 i + b, t = L & 3) the slots with b = 0 then hold the
+  // slice's first 128 k (step 2 ws) and the slots with b = 1 its second 128 k (step 2 ws + 1) OF THE SAME weight rows --
+  // different k in one MMA.  That is legal here because m = 1 leaves 7 of the 8 B-operand columns free: column 0 carries the
+  // activations of step 2 ws, column 1 those of step 2 ws + 1; slot r's result is valid in column b only (lane (r, t = 0),
+  // register c[b]).  The B fragments are loaded once per unit and serve both 16-row tiles.
+  const int grp = warp / GS_GW, ws = warp % GS_GW;
   const int li = lane >> 3, lc = lane & 7, lb = lc >> 2, q = lane & 3;
-  const uint32_t woff = uint32_t(li) * GS_ROW_BYTES + uint32_t(w) * GS_SLICE_BYTES + uint32_t(lc) * 16u;   // + 4 x rows per load
-  const uint32_t aoff = uint32_t(w) * 512u + uint32_t(lc) * 64u;    // lanes 0..7: the 32 activations of their own chunk
-  const int step_l = 2 * w + lb;                                       // this lane's 128-k step inside the unit
-  const uint32_t poff = uint32_t(step_l * 16 + li) * 8u;               // (c1, c2) of rows li (+4, +8, +12)
+  const uint32_t woff = uint32_t(li) * GS_ROW_BYTES + uint32_t(ws) * GS_SLICE_BYTES + uint32_t(lc) * 16u;   // + 4 x rows per load
+  const uint32_t aoff = uint32_t(ws) * 512u + uint32_t(lc) * 64u;     // lanes 0..7: the 32 activations of their own chunk
+  const int step_l = 2 * ws + lb;                                        // this lane's 128-k step inside the unit
+  const uint32_t poff = uint32_t(step_l * GS_ROWS + li) * 8u;            // (c1, c2) of rows li (+4, +8, ...)
   const uint32_t soff = uint32_t(step_l) * 8u;
+  const uint32_t redg = Rb + uint32_t(grp) * GS_RED_GROUP_BYTES;
+  const int nsl_last = (Kb - (UPR - 1) * GS_ROW_BYTES) / GS_SLICE_BYTES;   // valid K-slices of a row block's last unit
 
   uint32_t Rv[4][4];   // activations of the lane's chunk (lanes 0..7); other lanes feed unused MMA columns
 #pragma unroll
   for (int x = 0; x < 4; ++x)
 #pragma unroll
     for (int y = 0; y < 4; ++y) Rv[x][y] = 0u;
-
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows li, 8+li (pair 0), 4+li, 12+li (pair 1): this lane's k-half, column lb
-  int slot = 0, rbuf = 0;
-  uint32_t fphase = 0u;
-  int rb = t0 / UPR, ku = t0 - rb * UPR;
-  bool seg_from0 = (ku == 0);
-  const int nsl_last = (Kb - (UPR - 1) * (GS_NCONS * GS_SLICE_BYTES)) / GS_SLICE_BYTES;   // valid K-slices of a row block's last unit
-  uint32_t wst = Wb + woff, ast = Ab + aoff, pst = Pb + poff, sst = Sb + soff;
-  uint32_t fbar = Bb, ebar = Bb + 8u * uint32_t(3 * S);
-
-#pragma unroll 1
-  for (int t = t0; t < t1; ++t) {
-    const bool closes = (ku == UPR - 1);
-    gs_mbar_wait(fbar, fphase);
-    if ((!closes || w < nsl_last) && !(p.dbg & 1)) {
-      const float2 su = gs_lds64f(sst);
-      uint4 wv[4];
+  float acc[8];        // rows 16 tl + 4 ph + li and + 8 (pair index pr = 2 tl + ph): this lane's k-half, column lb
 #pragma unroll
-      for (int x = 0; x < 4; ++x) wv[x] = gs_lds128(wst + uint32_t(x) * (4u * GS_ROW_BYTES));
-      if (lane < 8) {   // one divergent region per stage
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+
+  // this group's first unit: the first t >= t0 with t % NG == grp; afterwards t -> t + NG is ku -> ku + 1 (wrapping into the next
+  // row block of the group), and -- S % NG == 0 -- the group's slot sequence closes on itself: no division per unit
+  int i = (grp - t0 % NG + NG) % NG;
+  int rb = 0, ku = 0;
+  if (i < n_units) unit_of(t0 + i, rb, ku);
+  int slot = i, rbuf = 0;
+  uint32_t fphase = 0u;
+  bool seg_from0 = false, seg_open = false;
+#pragma unroll 1
+  for (; i < n_units; i += NG) {
+    if (!seg_open) { seg_from0 = (ku == 0); seg_open = true; }
+    const bool closes = (ku == UPR - 1);
+    gs_mbar_wait(Bb + 8u * slot, fphase);   // weights + activations have landed
+    const bool active = (!closes || ws < nsl_last) && rb < p.NRB && !(p.dbg & 1);
+    float cc[4][4];
+    if (active) {
+      const uint32_t wst = Wb + uint32_t(slot) * GS_WBYTES + woff;
+      uint4 wv[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) wv[x] = gs_lds128(wst + uint32_t(x) * (4u * GS_ROW_BYTES));
+      if (lane < 8) {   // one divergent region per unit
+        const uint32_t ast = Ab + uint32_t(slot) * GS_ABYTES + aoff;
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
           const uint4 v = gs_lds128(ast + uint32_t(x) * 16u);
@@ -480,13 +496,13 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
       }
       __syncwarp();
 #pragma unroll
-      for (int pr = 0; pr < 2; ++pr) {
-        // rows (4 pr + li) -> fragment rows r, (8 + 4 pr + li) -> fragment rows r + 8
-        const float2 pa = gs_lds64f(pst + uint32_t(pr) * 32u);
-        const float2 pb = gs_lds64f(pst + uint32_t(pr) * 32u + 64u);
-        const uint32_t wa[4] = {wv[pr].x, wv[pr].y, wv[pr].z, wv[pr].w};
-        const uint32_t wb[4] = {wv[pr + 2].x, wv[pr + 2].y, wv[pr + 2].z, wv[pr + 2].w};
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int pr = 0; pr < 4; ++pr) {
+        // fragment rows r <- weight row 16 tl + 4 ph + li, rows r + 8 <- that row + 8
+        const int tl = pr >> 1, ph = pr & 1;
+        const uint32_t wa[4] = {wv[4 * tl + ph].x, wv[4 * tl + ph].y, wv[4 * tl + ph].z, wv[4 * tl + ph].w};
+        const uint32_t wb[4] = {wv[4 * tl + ph + 2].x, wv[4 * tl + ph + 2].y, wv[4 * tl + ph + 2].z, wv[4 * tl + ph + 2].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cc[pr][j] = 0.f;
 #pragma unroll
         for (int wi = 0; wi < 4; ++wi) {
           uint32_t ha[4], hb[4];
@@ -510,10 +526,24 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
               b0 = __byte_perm(Rv[wi][jj], Rv[wi][jj + 2], 0x5410);
               b1 = __byte_perm(Rv[wi][jj], Rv[wi][jj + 2], 0x7632);
             }
-            gs_mma<T>(c, af, b0, b1);
+            gs_mma<T>(cc[pr], af, b0, b1);
           }
         }
-        const float va = lb ? c[1] : c[0], vb = lb ? c[3] : c[2];   // column lb of fragment rows r / r + 8 (valid in lanes t = 0)
+      }
+    }
+    // the group parameters and activation sums are needed only now: the finisher works on THIS unit while we decode it, so its
+    // latency is off the critical path (with everything behind one barrier the consumers waited ~half the time although the
+    // feed alone ran at 0.84 of the roofline: profiles/r2_slab_v6_*.txt)
+    gs_mbar_wait(Bb + 8u * (S + slot), fphase);
+    if (active) {
+      const uint32_t pst = Pb + uint32_t(slot) * GS_PBYTES + poff;
+      const float2 su = gs_lds64f(Sb + uint32_t(slot) * GS_SBYTES + soff);
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        const int tl = pr >> 1, ph = pr & 1;
+        const float2 pa = gs_lds64f(pst + uint32_t(16 * tl + 4 * ph) * 8u);
+        const float2 pb = gs_lds64f(pst + uint32_t(16 * tl + 4 * ph + 8) * 8u);
+        const float va = lb ? cc[pr][1] : cc[pr][0], vb = lb ? cc[pr][3] : cc[pr][2];   // column lb of fragment rows r / r + 8 (valid in lanes t = 0)
         acc[2 * pr] = fmaf(pa.x, va - su.x, acc[2 * pr]);
         acc[2 * pr] = fmaf(pa.y, su.y, acc[2 * pr]);
         acc[2 * pr + 1] = fmaf(pb.x, vb - su.x, acc[2 * pr + 1]);
@@ -521,59 +551,64 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
       }
     }
     __syncwarp();
-    if (lane == 0) gs_mbar_arrive(ebar);
-    wst += GS_WBYTES; ast += GS_ABYTES; pst += GS_PBYTES; sst += GS_SBYTES; fbar += 8u; ebar += 8u;
-    if (++slot == S) {
-      slot = 0; fphase ^= 1u;
-      wst = Wb + woff; ast = Ab + aoff; pst = Pb + poff; sst = Sb + soff; fbar = Bb; ebar = Bb + 8u * uint32_t(3 * S);
-    }
+    if (lane == 0) gs_mbar_arrive(Bb + 8u * (3 * S + slot));
 
-    if (closes || t == t1 - 1) {
-      // ---- end of this range's segment of row block rb: CTA reduction over 8 K-slices x 2 k-halves, then store / park / collect ----
-      const uint32_t rbase = Rb + uint32_t(rbuf) * (2 * GS_NCONS * 16 * 4) + uint32_t(2 * w + lb) * 64u;
+    if (closes || i + NG >= n_units) {
+      // ---- end of this range's segment of row block rb: group reduction over 4 K-slices x 2 k-halves, then store / park / collect ----
+      const uint32_t rbase = redg + uint32_t(rbuf) * (2 * GS_GW * GS_ROWS * 4);
       if (q == 0) {
-        gs_sts32f(rbase + uint32_t(li) * 4u, acc[0]);
-        gs_sts32f(rbase + uint32_t(8 + li) * 4u, acc[1]);
-        gs_sts32f(rbase + uint32_t(4 + li) * 4u, acc[2]);
-        gs_sts32f(rbase + uint32_t(12 + li) * 4u, acc[3]);
+        const uint32_t rw = rbase + uint32_t(2 * ws + lb) * (GS_ROWS * 4u) + uint32_t(li) * 4u;
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {
+          gs_sts32f(rw + uint32_t(16 * (pr >> 1) + 4 * (pr & 1)) * 4u, acc[2 * pr]);
+          gs_sts32f(rw + uint32_t(16 * (pr >> 1) + 4 * (pr & 1) + 8) * 4u, acc[2 * pr + 1]);
+        }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(GS_NCONS * 32) : "memory");
-      if (threadIdx.x < 16) {
-        const int row = threadIdx.x;
-        const uint32_t rrow = Rb + uint32_t(rbuf) * (2 * GS_NCONS * 16 * 4) + uint32_t(row) * 4u;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GS_GW * 32) : "memory");
+      if (ws == 0) {
+        const int row = lane;
+        const int n = rb * GS_ROWS + row;
         float v = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < 2 * GS_NCONS; ++ww) v += gs_lds32f(rrow + uint32_t(ww) * 64u);
+        for (int ww = 0; ww < 2 * GS_GW; ++ww) v += gs_lds32f(rbase + uint32_t(ww) * (GS_ROWS * 4u) + uint32_t(row) * 4u);
+        unsigned long long* myslot = p.ws + (size_t(ri) * NG + grp) * GS_ROWS + row;
         if (!seg_from0) {
-          // contribution to a row block owned by a later range (only the first segment of a range can be one)
+          // contribution to a row block owned by a later range (only the first segment of a group's range can be one)
           const unsigned long long pk = (static_cast<unsigned long long>(p.nonce) << 32) | __float_as_uint(v);
-          asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.ws + size_t(ri) * 16 + row), "l"(pk) : "memory");
+          asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(myslot), "l"(pk) : "memory");
         } else {
           if (!closes) {
-            // this range owns the block but does not reach its end: add the parked sums of the ranges that cover the rest
-            const int rb_end = (rb + 1) * UPR;
+            // this range owns the block but does not reach its end: add the parked sums of the ranges that cover the rest.
+            // the block's last unit is t_last; range rj contributes iff it holds a unit of this row block
+            const int t_first = (t0 + i) - ku * NG;                 // the block's unit with ku = 0
+            const int t_last = t_first + (UPR - 1) * NG;
             for (int rj = ri + 1; rj < R; ++rj) {
               const int bj = gs_range_begin(rj, p.T, R), ej = gs_range_begin(rj + 1, p.T, R);
-              if (bj >= rb_end) break;
-              if (bj == ej) continue;
-              unsigned long long* sl = p.ws + size_t(rj) * 16 + row;
+              if (bj > t_last) break;
+              // first unit of this row block (t = t_first mod NG) inside [bj, ej)
+              const int tf = bj + ((t_first - bj) % NG + NG) % NG;
+              if (tf >= ej || tf > t_last) { if (ej > t_last) break; continue; }
+              unsigned long long* sl = p.ws + (size_t(rj) * NG + grp) * GS_ROWS + row;
               unsigned long long pk;
               do {
                 asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(pk) : "l"(sl) : "memory");
               } while (static_cast<unsigned int>(pk >> 32) != p.nonce);
               v += __uint_as_float(static_cast<unsigned int>(pk));
               asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(sl), "l"(0ull) : "memory");
-              if (ej >= rb_end) break;
+              if (ej > t_last) break;
             }
           }
-          gs_store<T>(p, rb * 16 + row, v);
+          if (n < p.N) gs_store<T>(p, n, v);
         }
       }
-      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       rbuf ^= 1;
-      seg_from0 = true;
+      seg_open = false;
     }
-    if (++ku == UPR) { ku = 0; ++rb; }
+    slot += NG;
+    if (slot >= S) { slot -= S; fphase ^= 1u; }
+    if (++ku == UPR) { ku = 0; rb += NG; }
   }
 }
 
@@ -612,7 +647,7 @@ bool get_w_map(CUtensorMap* tm, const void* W, int N, int K) {
   const cuuint64_t Kb = cuuint64_t(K) / 2;
   cuuint64_t dims[2] = {Kb / 4, cuuint64_t(N)};
   cuuint64_t strides[1] = {Kb};
-  cuuint32_t box[2] = {GS_ROW_BYTES / 4, 16};
+  cuuint32_t box[2] = {GS_ROW_BYTES / 4, GS_ROWS};
   cuuint32_t estr[2] = {1, 1};
   if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(W), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -628,7 +663,10 @@ bool get_w_map(CUtensorMap* tm, const void* W, int N, int K) {
   return true;
 }
 
-int gs_smem_bytes(int stages, int /*K*/) { return 1024 + stages * GS_STAGE_BYTES + GS_RED_BYTES + GS_MAX_STAGES * (32 + GS_SBYTES + GS_RAWBYTES) + 64; }
+
+int gs_smem_bytes(int stages, int NG) {
+  return 1024 + stages * (GS_WBYTES + GS_ABYTES + GS_PBYTES + GS_RAWBYTES + GS_SBYTES) + NG * GS_RED_GROUP_BYTES + 32 * stages + 64;
+}
 
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -638,7 +676,7 @@ int env_int(const char* name, int dflt) {
 constexpr int GS_MAX_DEVICES = BB_MAX_DEVICES;
 
 template <typename KernelT>
-int gs_occupancy(KernelT k, int variant, int smem, int dev) {
+int gs_occupancy(KernelT k, int variant, int threads, int smem, int dev) {
   // per (kernel variant, device): opt-in shared memory once (the device maximum); per dynamic size: occupancy, cached
   struct Entry { int smem, occ; };
   static std::mutex mu;
@@ -658,7 +696,7 @@ int gs_occupancy(KernelT k, int variant, int smem, int dev) {
   int& n = used[variant][dev];
   for (int i = 0; i < n; ++i) if (e[i].smem == smem) return e[i].occ;
   int o = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, GS_THREADS, size_t(smem)) != cudaSuccess) { cudaGetLastError(); o = 0; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, threads, size_t(smem)) != cudaSuccess) { cudaGetLastError(); o = 0; }
   const int occ = o < 1 ? -1 : o;
   const int slot = n < 8 ? n++ : 7;
   e[slot] = Entry{smem, occ};
@@ -667,7 +705,8 @@ int gs_occupancy(KernelT k, int variant, int smem, int dev) {
 
 }  // namespace
 
-size_t gemv_slab_workspace_bytes() { return size_t(GS_MAX_CPS) * size_t(device_sm_count()) * 16 * 8 + 256; }
+// tagged exchange slots: [CTAs][consumer groups][32 rows]; CTAs x groups <= 4 per SM in every configuration
+size_t gemv_slab_workspace_bytes() { return size_t(4) * size_t(device_sm_count()) * GS_ROWS * 8 + 256; }
 
 bool gemv_slab_supported(const bb_matmul_desc& d, int m) {
   if (m != 1) return false;
@@ -682,7 +721,7 @@ bool gemv_slab_supported(const bb_matmul_desc& d, int m) {
   if (d.w_fmt == BB_W_INT && d.with_zeros) return false;
   if (d.out_dtype != BB_F16 && d.out_dtype != BB_BF16 && d.out_dtype != BB_F32) return false;
   if (d.with_zeros && d.zeros_mode == BB_ZEROS_QUANTIZED && (d.N % 2)) return false;
-  if ((long long)(d.N / 16) * ((d.K + GS_KU - 1) / GS_KU) >= (1ll << 30)) return false;
+  if ((long long)((d.N + GS_ROWS - 1) / GS_ROWS + 4) * ((d.K + GS_KU - 1) / GS_KU) >= (1ll << 30)) return false;
   return true;   // (a missing cuTensorMapEncodeTiled entry point is reported loudly at launch, not hidden behind a fallback)
 }
 
@@ -697,6 +736,8 @@ int launch_gemv_slab(const MatmulArgs& a) {
     return 5;
   }
   const int dev = current_device();
+  // consumer groups per CTA x CTAs per SM: (4, 1) shares one deep ring between four groups, (2, 2) runs two CTAs per SM
+  const int ng = env_int("BB_GS_NG", 2) == 4 ? 4 : 2;
   SlabParams p;
   p.A = a.A; p.scale = d.with_scaling ? a.scale : nullptr; p.zeros = d.with_zeros ? a.zeros : nullptr;
   p.bias = d.with_bias ? a.bias : nullptr; p.out = make_outspec(a);
@@ -706,37 +747,38 @@ int launch_gemv_slab(const MatmulArgs& a) {
   p.zp_const = (d.w_fmt == BB_W_INT) ? (1 << (d.w_bits - 1)) : 0;
   p.out_dtype = d.out_dtype;
   p.UPR = (d.K + GS_KU - 1) / GS_KU;
-  p.T = (d.N / 16) * p.UPR;
-  int stages = env_int("BB_GS_STAGES", 4);
-  stages = std::max(2, std::min(GS_MAX_STAGES, stages));
+  p.NRB = (d.N + GS_ROWS - 1) / GS_ROWS;
+  p.T = ((p.NRB + ng - 1) / ng) * p.UPR * ng;
+  // the ring depth must be a multiple of the group count: slot s then always belongs to group s % NG, which therefore sees every
+  // phase of the slot's barriers (a group that skipped a phase would mistake the parity of a later one for its own)
+  int stages = env_int("BB_GS_STAGES", ng == 4 ? 8 : 4);
+  stages = std::max(ng, std::min(GS_MAX_STAGES, stages) / ng * ng);
   p.stages = stages;
-  p.W = reinterpret_cast<const uint8_t*>(a.W);
   p.dbg = env_int("BB_GS_DBG", 0);
   CUtensorMap tm;
   if (!get_w_map(&tm, a.W, d.N, d.K)) { set_error("gemv_slab: cuTensorMapEncodeTiled failed"); return 4; }
-  p.fast_params = (p.g128 == 1 && (p.G & 7) == 0 && (!d.with_scaling || (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0) &&
+  p.fast_params = (p.g128 == 1 && (p.G & 7) == 0 && (d.N % GS_ROWS) == 0 &&
+                   (!d.with_scaling || (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0) &&
                    (!d.with_zeros || (reinterpret_cast<uintptr_t>(a.zeros) & 15) == 0)) ? 1 : 0;
   p.ws = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(a.workspace) + 15) & ~uintptr_t(15));
   static std::atomic<unsigned int> counter{0x9e3779b9u};
   unsigned int nz = counter.fetch_add(0x9e3779b9u);
   p.nonce = nz | 1u;
-  int cps = env_int("BB_GS_CPS", 2);
-  cps = std::max(1, std::min(GS_MAX_CPS, cps));
   const bool il = d.w_layout == BB_LAYOUT_INTERLEAVED_16;
   const bool f16 = d.a_dtype == BB_F16;
-  const int smem = gs_smem_bytes(stages, d.K);
+  const int smem = gs_smem_bytes(stages, ng);
   const int sms = device_sm_count();
   static const bool pdl = [] { const char* e = getenv("BB_PDL"); return e ? atoi(e) != 0 : true; }();
 
-#define BB_GS_GO(TT, ILV, CPSV, VAR)                                                                   \
+#define BB_GS_GO(TT, ILV, NGV, MINBV, VAR)                                                             \
   {                                                                                                    \
-    auto k = gemv_slab_kernel<TT, ILV, CPSV>;                                                          \
-    int occ = gs_occupancy(k, VAR, smem, dev);                                                       \
-    if (occ < 0) { set_error("gemv_slab: kernel does not fit on this device (stages=%d, K=%d)", stages, d.K); return 4; } \
-    occ = std::min(occ, CPSV);                                                                         \
+    auto k = gemv_slab_kernel<TT, ILV, NGV, MINBV>;                                                    \
+    int occ = gs_occupancy(k, VAR, gs_threads(NGV), smem, dev);                                        \
+    if (occ < 0) { set_error("gemv_slab: kernel does not fit on this device (stages=%d)", stages); return 4; } \
+    occ = std::min(occ, MINBV);                                                                        \
     const int grid = std::max(1, std::min(p.T, occ * sms));                                            \
     cudaLaunchConfig_t cfg = {};                                                                       \
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GS_THREADS);                                         \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gs_threads(NGV));                                    \
     cfg.dynamicSmemBytes = smem; cfg.stream = a.stream;                                                \
     cudaLaunchAttribute attr[1];                                                                       \
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                   \
@@ -744,13 +786,12 @@ int launch_gemv_slab(const MatmulArgs& a) {
     cfg.attrs = attr; cfg.numAttrs = 1;                                                                \
     BB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, tm, p));                                                 \
   }
-#define BB_GS_CPS(TT, ILV, VB)                                  \
-  if (cps == 1) BB_GS_GO(TT, ILV, 1, VB + 0)                    \
-  else if (cps == 2) BB_GS_GO(TT, ILV, 2, VB + 1)               \
-  else BB_GS_GO(TT, ILV, 3, VB + 2)
-  if (f16) { if (il) { BB_GS_CPS(__half, true, 0) } else { BB_GS_CPS(__half, false, 3) } }
-  else { if (il) { BB_GS_CPS(__nv_bfloat16, true, 6) } else { BB_GS_CPS(__nv_bfloat16, false, 9) } }
-#undef BB_GS_CPS
+#define BB_GS_NG(TT, ILV, VB)                                    \
+  if (ng == 4) BB_GS_GO(TT, ILV, 4, 1, VB + 0)                   \
+  else BB_GS_GO(TT, ILV, 2, 2, VB + 1)
+  if (f16) { if (il) { BB_GS_NG(__half, true, 0) } else { BB_GS_NG(__half, false, 2) } }
+  else { if (il) { BB_GS_NG(__nv_bfloat16, true, 4) } else { BB_GS_NG(__nv_bfloat16, false, 6) } }
+#undef BB_GS_NG
 #undef BB_GS_GO
   BB_LAUNCH_CHECK();
   return 0;

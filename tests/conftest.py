@@ -21,7 +21,8 @@ def pytest_collection_modifyitems(config, items):
         if config.pluginmanager.hasplugin("timeout"):
             for item in items:
                 if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
-                    item.add_marker(pytest.mark.timeout(300))
+                    item.add_marker(pytest.mark.timeout(180, method="thread"))   # "thread": a test blocked inside a CUDA call
+                                                                                   # (a hung kernel) cannot be interrupted by a signal
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

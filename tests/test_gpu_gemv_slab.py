@@ -72,13 +72,15 @@ def test_gemv_slab_parity(kw):
     assert torch.equal(got, got2)
 
 
-@pytest.mark.parametrize("stages,cps", [(2, 1), (3, 3), (6, 1), (4, 2), (2, 3)])
-def test_gemv_slab_knobs(stages, cps):
-    """ring depth and CTAs per SM give the same answer (the stream-K boundaries move with the grid size)."""
-    case = H.make_case(1, 4112, 6144, with_bias=True, **Q)
+@pytest.mark.parametrize("stages,groups", [(4, 4), (8, 4), (2, 2), (4, 2), (6, 2)])
+@pytest.mark.parametrize("N,K", [(4112, 6144), (96, 11264)])
+def test_gemv_slab_knobs(stages, groups, N, K):
+    """ring depth and consumer groups per CTA (4 groups x 1 CTA per SM, 2 groups x 2 CTAs per SM) give the same answer: the
+    stream-K boundaries and the padding units past the last row block move with the grid and the group count."""
+    case = H.make_case(1, N, K, with_bias=True, **Q)
     ref = H.oracle_output(case, fast_decoding=True)
-    _, got = _slab(case, BB_GS_STAGES=stages, BB_GS_CPS=cps)
-    H.assert_fp_close(got, ref, f"gemv_slab stages={stages} cps={cps}")
+    _, got = _slab(case, BB_GS_STAGES=stages, BB_GS_NG=groups)
+    H.assert_fp_close(got, ref, f"gemv_slab stages={stages} groups={groups}")
 
 
 # BASELINE.json configs[1] (C1: W4A16 GEMV M=1 on the Llama-2-70B linears) + the 12288^2 target shape, full output vs the oracle

@@ -2,7 +2,7 @@
 // dequantise+dot, then back-to-back timing over rotating weight copies (cold L2), for a list of shapes and tuning knobs.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/gemv_bench tools/gemv_bench.cu \
 //        -Lbitblas_b200/lib -lbitblas_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../bitblas_b200/lib'
-//   tools/gemv_bench [--kernel ID] [--iters N] [--cfg STAGES,CPS,FLAVOR]... [--nocheck] NxK [NxK ...]
+//   tools/gemv_bench [--kernel ID] [--iters N] [--cfg STAGES,GROUPS]... [--nocheck] NxK [NxK ...]
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -20,7 +20,7 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 #define BB(x) do { int rc = (x); if (rc) { printf("bb error %d at line %d: %s\n", rc, __LINE__, bb_last_error()); exit(1);} } while (0)
 
-struct Cfg { int stages, cps, flavor; };
+struct Cfg { int stages, ng; };
 
 int main(int argc, char** argv) {
   int kernel = BB_KERNEL_AUTO, iters = 200;
@@ -32,11 +32,11 @@ int main(int argc, char** argv) {
     if (a == "--kernel") kernel = atoi(argv[++i]);
     else if (a == "--iters") iters = atoi(argv[++i]);
     else if (a == "--nocheck") check = false;
-    else if (a == "--cfg") { Cfg c{4, 2, -1}; sscanf(argv[++i], "%d,%d,%d", &c.stages, &c.cps, &c.flavor); cfgs.push_back(c); }
+    else if (a == "--cfg") { Cfg c{4, 2}; sscanf(argv[++i], "%d,%d", &c.stages, &c.ng); cfgs.push_back(c); }
     else { int n, k; if (sscanf(a.c_str(), "%dx%d", &n, &k) == 2) shapes.push_back({n, k}); }
   }
   if (shapes.empty()) shapes.push_back({12288, 12288});
-  if (cfgs.empty()) cfgs.push_back(Cfg{4, 2, -1});
+  if (cfgs.empty()) cfgs.push_back(Cfg{4, 2});
   BB(bb_init(0));
   bb_set_kernel_override(kernel);
   cudaStream_t st; CK(cudaStreamCreate(&st));
@@ -98,8 +98,7 @@ int main(int argc, char** argv) {
     for (const Cfg& c : cfgs) {
       char buf[32];
       snprintf(buf, 32, "%d", c.stages); setenv("BB_GS_STAGES", buf, 1);
-      snprintf(buf, 32, "%d", c.cps); setenv("BB_GS_CPS", buf, 1);
-      if (c.flavor >= 0) { snprintf(buf, 32, "%d", c.flavor); setenv("BB_GS_FLAVOR", buf, 1); } else unsetenv("BB_GS_FLAVOR");
+      snprintf(buf, 32, "%d", c.ng); setenv("BB_GS_NG", buf, 1);
       double maxerr = -1, maxref = 0;
       if (check) {
         CK(cudaMemset(dC, 0xff, N * 2));
@@ -129,8 +128,8 @@ int main(int argc, char** argv) {
         best = std::min(best, ms / iters); sum += ms / iters;
       }
       const double us_best = best * 1e3, us_mean = sum / reps * 1e3;
-      printf("N=%d K=%d kernel=%s stages=%d cps=%d flavor=%d : %.2f us best %.2f us mean  %.0f GB/s  frac(6576)=%.3f  maxerr=%.3g (max|ref|=%.3g)\n",
-             N, K, bb_kernel_name(kid), c.stages, c.cps, c.flavor, us_best, us_mean, alg / (us_mean * 1e-6) / 1e9,
+      printf("N=%d K=%d kernel=%s stages=%d groups=%d : %.2f us best %.2f us mean  %.0f GB/s  frac(6576)=%.3f  maxerr=%.3g (max|ref|=%.3g)\n",
+             N, K, bb_kernel_name(kid), c.stages, c.ng, us_best, us_mean, alg / (us_mean * 1e-6) / 1e9,
              alg / (us_mean * 1e-6) / 1e9 / 6576.1, maxerr, maxref);
       fflush(stdout);
     }
