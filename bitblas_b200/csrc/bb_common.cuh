@@ -188,6 +188,17 @@ template <>
 __device__ __forceinline__ uint32_t mul2<__nv_bfloat16>(uint32_t a, uint32_t b) {
   return b2_as_u32(__hmul2(u32_as_b2(a), u32_as_b2(b)));
 }
+// a * b - c with TWO roundings (the _rn intrinsics are never contracted into an fma by the compiler)
+template <typename T>
+__device__ __forceinline__ uint32_t mul_then_sub2(uint32_t a, uint32_t b, uint32_t c);
+template <>
+__device__ __forceinline__ uint32_t mul_then_sub2<__half>(uint32_t a, uint32_t b, uint32_t c) {
+  return h2_as_u32(__hsub2_rn(__hmul2_rn(u32_as_h2(a), u32_as_h2(b)), u32_as_h2(c)));
+}
+template <>
+__device__ __forceinline__ uint32_t mul_then_sub2<__nv_bfloat16>(uint32_t a, uint32_t b, uint32_t c) {
+  return b2_as_u32(__hsub2_rn(__hmul2_rn(u32_as_b2(a), u32_as_b2(b)), u32_as_b2(c)));
+}
 template <typename T>
 __device__ __forceinline__ uint32_t fma2(uint32_t a, uint32_t b, uint32_t c);
 template <>
@@ -210,14 +221,18 @@ struct DqConst {
   uint32_t z2, s2, negz2;
 };
 // raw "magic + u" pair -> dequantised A_dtype pair, in A_dtype arithmetic with the reference's rounding order
-// (bitblas/gpu/intrin/lop3.py:172-175 sub then mul; :256,269 rescale = one fma).  MODE: 0 none, 1 scale, 2 "original"
-// zeros, 3 "rescale" zeros, 4 quantized zeros (integer zero point folded into mz).
-template <typename T, int MODE>
+// (bitblas/gpu/intrin/lop3.py:172-175 sub then mul; rescale: ONE fma for 4-bit (:256,269) but mul THEN sub -- two roundings --
+// for 2-bit (:633-635); both orders are kept).  MODE: 0 none, 1 scale, 2 "original" zeros, 3 "rescale" zeros, 4 quantized zeros
+// (integer zero point folded into mz).
+template <typename T, int MODE, int BITS = 4>
 __device__ __forceinline__ uint32_t dq_finish(uint32_t x, uint32_t mz, const DqConst& c) {
   const uint32_t t = sub2<T>(x, mz);
   if constexpr (MODE == 1 || MODE == 4) return mul2<T>(t, c.s2);
   if constexpr (MODE == 2) return mul2<T>(sub2<T>(t, c.z2), c.s2);
-  if constexpr (MODE == 3) return fma2<T>(t, c.s2, c.negz2);
+  if constexpr (MODE == 3) {
+    if constexpr (BITS == 2) return mul_then_sub2<T>(t, c.s2, c.z2);
+    else return fma2<T>(t, c.s2, c.negz2);
+  }
   return t;
 }
 

@@ -223,7 +223,7 @@ template <typename T, int BITS, int MODE, bool IL>
 __device__ __forceinline__ void dequant_half_row(uint32_t src, uint32_t (&out)[16], const DqConst& c) {
   constexpr bool HI = IL && std::is_same<T, __half>::value && BITS == 4;
   constexpr uint32_t M = TypeTraits<T>::kMagic;
-  auto fin = [&](uint32_t x, uint32_t mz) -> uint32_t { return dq_finish<T, MODE>(x, mz, c); };
+  auto fin = [&](uint32_t x, uint32_t mz) -> uint32_t { return dq_finish<T, MODE, BITS>(x, mz, c); };
   if constexpr (BITS == 4) {
     const uint4 pk = lds128(src);
     const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};

@@ -33,9 +33,10 @@ namespace {
 
 constexpr int MAX_KS = 8;  // warps per CTA = K splits per 16-row block
 constexpr int PF = 4;      // weight steps in flight per warp (register queue of plain 128-bit ld.global.nc loads).
-                           // tools/membench.cu on B200, 12288^2 weights: this pattern (16 rows x 64 B per warp load,
-                           // depth 4, 3-4 K-splits) streams at 6.0-6.7 TB/s; the same addresses through cp.async
-                           // (LDGSTS) saturate at ~4.3 TB/s, a depth-8 queue at ~4.0 TB/s.
+                           // tools/membench.cu on B200, 12288^2 weights (profiles/r2_membench.txt): this pattern (16 rows x
+                           // 64 B per warp load, depth 4, 3 K-splits) reads at the linear-read rate (15.0 us per 75.5 MB
+                           // launch, of which ~4 us are launch gap and tail); the same addresses through cp.async (LDGSTS)
+                           // take 17.3 us, a depth-8 queue 17.2 us.
 
 struct GemvParams {
   const void* A;

@@ -132,7 +132,7 @@ __global__ void debug_dequant16_kernel(int bits, int zp, int layout, const uint3
       c.s2 = MODE != 0 ? dup2<T>(scale[g]) : 0u;
       c.z2 = (MODE == 2 || MODE == 3) ? dup2<T>(zeros[g]) : 0u;
       c.negz2 = c.z2 ^ 0x80008000u;
-      const uint32_t v = dq_finish<T, MODE>(h[j], c.mz_lo, c);
+      const uint32_t v = bits == 2 ? dq_finish<T, MODE, 2>(h[j], c.mz_lo, c) : dq_finish<T, MODE, 4>(h[j], c.mz_lo, c);
       r[e] = e == 0 ? uint16_t(v & 0xffff) : uint16_t(v >> 16);
     }
     out[size_t(per_word) * i + i0] = *reinterpret_cast<const T*>(&r[0]);

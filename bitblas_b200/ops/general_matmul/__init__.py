@@ -255,10 +255,14 @@ class Matmul(Operator):
         self._desc = None
         self._ws = {}
         self._ws_need = {}
+        self._checked_key = None
+        self._torch_a_dtype = getattr(torch, config.A_dtype, None)
+        self._desc_ref = None
         self.weight_executors = None
         self.input_executors = None
         if not self.consistent:
             self._desc = self._make_desc()
+            self._desc_ref = ctypes.byref(self._desc)
             if bit in (1, 2, 4):
                 tgt = 0
                 if self.fast_decoding:
@@ -346,14 +350,10 @@ class Matmul(Operator):
         if numel is not None and t.numel() != numel:
             raise ValueError(f"{name} has {t.numel()} elements, expected {numel}")
 
-    def forward(self, A, W, scale=None, zeros=None, bias=None, output=None) -> Any:
-        if self.consistent:
-            return self._forward_consistent(A, W, bias, output)
+    def _check_params(self, W, scale, zeros, bias):
+        """full validation of the (static) parameter tensors; forward() runs it once per distinct set of tensors."""
         c = self.config
         adt = getattr(torch, c.A_dtype)
-        self._check_tensor(A, "A", adt)
-        if A.shape[-1] != c.K:
-            raise ValueError(f"A has inner dimension {A.shape[-1]}, expected K={c.K}")
         wshape = self.retrieve_weight_shape()
         self._check_tensor(W, "W", torch.int8 if W.dtype != torch.uint8 else torch.uint8, wshape[0] * wshape[1])
         G = c.K // (c.group_size if c.group_size and c.group_size > 0 else c.K)
@@ -372,31 +372,51 @@ class Matmul(Operator):
             if bias is None:
                 raise ValueError("with_bias=True but bias is None")
             self._check_tensor(bias, "bias", adt, c.N)
-        m = reduce(_operator.mul, A.shape[:-1], 1)
+
+    def forward(self, A, W, scale=None, zeros=None, bias=None, output=None) -> Any:
+        if self.consistent:
+            return self._forward_consistent(A, W, bias, output)
+        c = self.config
+        # the parameter tensors of a layer do not change between calls: validate each distinct set once (keyed on the storage
+        # pointers; a new tensor -- or a re-allocated one -- is validated again).  The activations are checked every call.
+        key = (W.data_ptr(), scale.data_ptr() if scale is not None else 0, zeros.data_ptr() if zeros is not None else 0,
+               bias.data_ptr() if bias is not None else 0)
+        if key != self._checked_key:
+            self._check_params(W, scale, zeros, bias)
+            self._checked_key = key
+        if not (A.is_cuda and A.dtype == self._torch_a_dtype and A.is_contiguous()):
+            self._check_tensor(A, "A", self._torch_a_dtype)
+        K = c.K
+        if A.shape[-1] != K:
+            raise ValueError(f"A has inner dimension {A.shape[-1]}, expected K={K}")
+        m = A.numel() // K
         if self.dynamic_range is None and m != int(c.M):
             raise ValueError(f"operator was created for static M={c.M}, got {m} rows")
+        dev = A.device
         if output is None:
-            output = torch.empty(A.shape[:-1] + (c.N,), dtype=self.torch_output_dtype, device=A.device)
-        else:
+            output = torch.empty(A.shape[:-1] + (c.N,), dtype=self.torch_output_dtype, device=dev)
+        elif not (output.is_cuda and output.dtype == self.torch_output_dtype and output.is_contiguous() and output.numel() == m * c.N):
             self._check_tensor(output, "output", self.torch_output_dtype, m * c.N)
-        dev = A.device.index if A.device.index is not None else torch.cuda.current_device()
-        _lib.ensure_init(dev)
-        stream = torch.cuda.current_stream(device=A.device).cuda_stream
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if idx not in _lib._inited:
+            _lib.ensure_init(idx)
+        stream = torch.cuda.current_stream(dev).cuda_stream
         lut = self.lut
-        if lut is not None and lut.device != A.device:
-            lut = self.lut = lut.to(A.device)
-        ws_ptr, ws_bytes = self._workspace_for(int(m), A.device)
-        rc = self.lib._c.bb_matmul(ctypes.byref(self._desc), A.data_ptr(), W.data_ptr(),
-                                   lut.data_ptr() if lut is not None else 0,
-                                   scale.data_ptr() if c.with_scaling else 0,
-                                   zeros.data_ptr() if c.with_zeros else 0,
-                                   bias.data_ptr() if c.with_bias else 0,
-                                   output.data_ptr(), int(m), ws_ptr, ws_bytes, stream)
+        if lut is not None and lut.device != dev:
+            lut = self.lut = lut.to(dev)
+        ws_ptr, ws_bytes = self._workspace_for(m, dev, stream)
+        if idx != torch.cuda.current_device():
+            with torch.cuda.device(dev):   # the kernels launch on the calling thread's current device
+                rc = self.lib._c.bb_matmul(self._desc_ref, A.data_ptr(), key[0], lut.data_ptr() if lut is not None else 0,
+                                           key[1], key[2], key[3], output.data_ptr(), m, ws_ptr, ws_bytes, stream)
+        else:
+            rc = self.lib._c.bb_matmul(self._desc_ref, A.data_ptr(), key[0], lut.data_ptr() if lut is not None else 0,
+                                       key[1], key[2], key[3], output.data_ptr(), m, ws_ptr, ws_bytes, stream)
         if rc != 0:
             raise RuntimeError(f"bb_matmul failed (code {rc}): {_lib.last_error()}")
         return output
 
-    def _workspace_for(self, m: int, device):
+    def _workspace_for(self, m: int, device, stream=None):
         """scratch the kernel picked for `m` needs (bb_workspace_bytes: split-K partials, stream-K exchange slots); one cached,
         ZERO-INITIALISED buffer per operator, device and stream, grown on demand.  The stream-K kernels leave their slots
         zero-tagged, so the buffer is reused by later calls on the same stream without clearing (include/bitblas_b200.h)."""
@@ -406,7 +426,7 @@ class Matmul(Operator):
             need = self._ws_need[key] = int(self.lib._c.bb_workspace_bytes(ctypes.byref(self._desc), int(m)))
         if need == 0:
             return 0, 0
-        wkey = (device, torch.cuda.current_stream(device).cuda_stream)
+        wkey = (device, stream if stream is not None else torch.cuda.current_stream(device).cuda_stream)
         ws = self._ws.get(wkey)
         if ws is None or ws.numel() < need:
             ws = torch.zeros(need, dtype=torch.uint8, device=device)

@@ -172,7 +172,8 @@ def test_dequant_arithmetic_vs_reference_device_functions(kind, bits, mode):
     # and the oracle's A_dtype dequantise (the model every parity test is checked against) states the same numbers
     u = torch.from_numpy(vals.reshape(-1).astype(np.float32)).half()
     s8, z8, q8 = (scale.cpu().repeat_interleave(8), zeros.cpu().repeat_interleave(8), qz.cpu().repeat_interleave(8).half())
-    expect = {1: u * s8, 2: (u - z8) * s8, 3: torch.addcmul(-z8.float(), u.float(), s8.float()).half(), 4: (u - q8) * s8}[mode]
+    rescale = (u * s8 - z8) if bits == 2 else torch.addcmul(-z8.float(), u.float(), s8.float()).half()   # 2-bit: two roundings (lop3.py:633-635)
+    expect = {1: u * s8, 2: (u - z8) * s8, 3: rescale, 4: (u - q8) * s8}[mode]
     assert torch.equal(mine.cpu(), expect)
 
 

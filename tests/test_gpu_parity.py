@@ -424,3 +424,51 @@ def test_gptq_repack_v2_module(bits, m):
             assert torch.equal(lin.zeros.cpu(), torch.from_numpy(O.general_compress(zint.to(torch.int8).numpy(), bits)))
         got = lin(A.cuda()).cpu()
         H.assert_fp_close(got, ref, f"gptq-v2 {mode} bits={bits} m={m}")
+
+
+# ---- BASELINE.json configs[2] / [3] at their real shapes: W4A16 GEMM M in {16, 128, 4096} on the Llama-2-70B linears and the
+# 12288^2 target, W2A8 INT32 at 12288^2 (mirrors testing/python/operators/test_general_matmul_ops_backend_tl.py:127-283) --------
+_BASELINE_NK = [(8192, 8192), (28672, 8192), (8192, 28672), (12288, 12288)]
+
+
+@pytest.mark.parametrize("N,K", _BASELINE_NK, ids=lambda v: str(v))
+def test_gemm_ts_baseline_shapes(N, K):
+    """one weight matrix per shape, M = 16 / 128 (every output row) and M = 4096 (64 sampled rows x all N columns: the oracle's
+    CPU matmul on all 4096 rows would take minutes); GPTQ-style quantized zeros, group 128."""
+    import bitblas_oracle as O
+    import bitblas_b200 as bitblas
+    g = torch.Generator().manual_seed(N + K)
+    fields = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int8)
+    scale = (torch.rand((N, K // 128), generator=g) * 0.125 + 0.01).half()
+    zq = torch.randint(0, 16, (K // 128, N), generator=g, dtype=torch.int8)
+    qz = torch.from_numpy(O.general_compress(zq.numpy(), 4))
+    cfg = bitblas.MatmulConfig(M=[16, 128, 4096], N=N, K=K, A_dtype="float16", W_dtype="uint4", accum_dtype="float16",
+                               out_dtype="float16", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized")
+    op = bitblas.Matmul(cfg, enable_tuning=False)
+    W = op.transform_weight(fields.cuda())
+    sc, zz = scale.cuda(), qz.cuda()
+    Wd = O.dequantize_weight(fields.to(torch.int32), W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True,
+                             zeros_mode="quantized", scale=scale, zeros=qz).float()
+    for M in (16, 128, 4096):
+        assert op.kernel_for(M) == "gemm_ts_tcgen05"
+        A = (torch.rand((M, K), generator=g) - 0.5).half()
+        got = op.forward(A.cuda(), W, scale=sc, zeros=zz).cpu()
+        rows = torch.arange(M) if M <= 128 else torch.randperm(M, generator=g)[:64].sort().values
+        ref = (A[rows].float() @ Wd.t()).half()
+        H.assert_fp_close(got[rows], ref, f"gemm_ts M={M} {N}x{K}")
+
+
+@pytest.mark.parametrize("M", [1, 128])
+def test_w2a8_baseline_shape(M):
+    """BASELINE configs[3]: W2A8 (BitNet b1.58: int8 activations x ternary int2 weights), int32 accumulate, N = K = 12288: exact."""
+    import bitblas_b200 as bitblas
+    N = K = 12288
+    g = torch.Generator().manual_seed(5)
+    Wt = torch.randint(-1, 2, (N, K), generator=g, dtype=torch.int8)
+    A = torch.randint(-128, 128, (M, K), generator=g, dtype=torch.int8)
+    cfg = bitblas.MatmulConfig(M=M, N=N, K=K, A_dtype="int8", W_dtype="int2", accum_dtype="int32", out_dtype="int32")
+    op = bitblas.Matmul(cfg, enable_tuning=False)
+    W = op.transform_weight(Wt.cuda())
+    got = op.forward(A.cuda(), W).cpu()
+    ref = (A.double() @ Wt.double().t()).to(torch.int32)   # |sum| <= 12288 * 128: exact in float64
+    assert torch.equal(got, ref)
