@@ -62,6 +62,9 @@ constexpr int GS_SBYTES = GS_STEPS * 8;             // (SM, S) fp32 pairs [step]
 constexpr int GS_RAWBYTES = 1024;                   // raw scales [32 rows][8 groups] fp16 + raw zeros (fp16 [32][8] or packed [8 groups][16 B])
 constexpr int GS_RED_GROUP_BYTES = 2 * (2 * GS_GW) * GS_ROWS * 4;   // per group: two buffers x (4 warps x 2 k-halves) partials x 32 rows
 constexpr int GS_MAX_STAGES = 10;
+constexpr uint32_t GS_SUSPEND_NS = 20000;   // try_wait suspend-time hint: a waiting warp sleeps in hardware until the phase flips
+                                             // instead of re-issuing the probe (the default limit re-issued it ~12 times per wait: 14 %
+                                             // of all issued instructions were wait-loop instructions)
 
 __host__ __device__ constexpr int gs_threads(int NG) { return (GS_GW * NG + 1 + NG / 2) * 32; }
 
@@ -107,11 +110,11 @@ __device__ __forceinline__ void gs_mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "GS_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra GS_DONE_%=;\n"
       "bra GS_WAIT_%=;\n"
       "GS_DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
+      "}\n" ::"r"(bar), "r"(parity), "r"(GS_SUSPEND_NS) : "memory");
 }
 __device__ __forceinline__ void gs_tma_2d(uint32_t dst, const void* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
@@ -201,8 +204,10 @@ __device__ __forceinline__ void gs_store(const SlabParams& p, int n, float v) {
 __device__ __forceinline__ int gs_range_begin(int ri, int T, int R) { return int((long long)ri * T / R); }
 
 
-// NG consumer groups per CTA, MINB CTAs per SM: (2, 2) or (4, 1)
-template <typename T, bool IL, int NG, int MINB>
+// NG consumer groups per CTA, MINB CTAs per SM: (2, 2) or (4, 1).  SC = ring depth as a compile-time constant (0: p.stages at run
+// time, the tuning / test variant): with a constant depth every stage address is base + immediate -- the run-time variant spends
+// ~40 integer instructions per unit and warp re-deriving the region bases (profiles/r2_gemv_slab_ncu_full.txt, SASS page)
+template <typename T, bool IL, int NG, int MINB, int SC>
 __global__ void __launch_bounds__(gs_threads(NG), MINB)
 gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   constexpr bool F16 = std::is_same<T, __half>::value;
@@ -212,7 +217,7 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   constexpr int NF = NG / 2;                 // finisher warps
   constexpr int NCW = GS_GW * NG;            // consumer warps
   extern __shared__ uint8_t gs_raw[];
-  const int S = p.stages;
+  const int S = SC > 0 ? SC : p.stages;
   const uint32_t base = (gs_smem_u32(gs_raw) + 1023u) & ~1023u;
   const uint32_t Wb = base;                                   // [S][32 rows][512 B]
   const uint32_t Ab = Wb + uint32_t(S) * GS_WBYTES;           // [S][1024 halves]
@@ -770,9 +775,9 @@ int launch_gemv_slab(const MatmulArgs& a) {
   const int sms = device_sm_count();
   static const bool pdl = [] { const char* e = getenv("BB_PDL"); return e ? atoi(e) != 0 : true; }();
 
-#define BB_GS_GO(TT, ILV, NGV, MINBV, VAR)                                                             \
+#define BB_GS_GO(TT, ILV, NGV, MINBV, SCV, VAR)                                                        \
   {                                                                                                    \
-    auto k = gemv_slab_kernel<TT, ILV, NGV, MINBV>;                                                    \
+    auto k = gemv_slab_kernel<TT, ILV, NGV, MINBV, SCV>;                                               \
     int occ = gs_occupancy(k, VAR, gs_threads(NGV), smem, dev);                                        \
     if (occ < 0) { set_error("gemv_slab: kernel does not fit on this device (stages=%d)", stages); return 4; } \
     occ = std::min(occ, MINBV);                                                                        \
@@ -786,11 +791,14 @@ int launch_gemv_slab(const MatmulArgs& a) {
     cfg.attrs = attr; cfg.numAttrs = 1;                                                                \
     BB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, tm, p));                                                 \
   }
+  // the shipped configuration (2 groups, 4 stages) has the ring depth compiled in; every other knob setting runs the run-time-depth
+  // variants (tuning sweeps, tests of the ring logic)
 #define BB_GS_NG(TT, ILV, VB)                                    \
-  if (ng == 4) BB_GS_GO(TT, ILV, 4, 1, VB + 0)                   \
-  else BB_GS_GO(TT, ILV, 2, 2, VB + 1)
-  if (f16) { if (il) { BB_GS_NG(__half, true, 0) } else { BB_GS_NG(__half, false, 2) } }
-  else { if (il) { BB_GS_NG(__nv_bfloat16, true, 4) } else { BB_GS_NG(__nv_bfloat16, false, 6) } }
+  if (ng == 4) BB_GS_GO(TT, ILV, 4, 1, 0, VB + 0)                \
+  else if (stages == 4) BB_GS_GO(TT, ILV, 2, 2, 4, VB + 1)       \
+  else BB_GS_GO(TT, ILV, 2, 2, 0, VB + 2)
+  if (f16) { if (il) { BB_GS_NG(__half, true, 0) } else { BB_GS_NG(__half, false, 3) } }
+  else { if (il) { BB_GS_NG(__nv_bfloat16, true, 6) } else { BB_GS_NG(__nv_bfloat16, false, 9) } }
 #undef BB_GS_NG
 #undef BB_GS_GO
   BB_LAUNCH_CHECK();
