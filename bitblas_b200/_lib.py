@@ -17,6 +17,8 @@ BB_F16, BB_BF16, BB_F32, BB_I8, BB_I32 = 0, 1, 2, 3, 4
 BB_W_UINT, BB_W_INT, BB_W_NF, BB_W_FP4, BB_W_FP8_E4M3, BB_W_FP8_E5M2 = 0, 1, 2, 3, 4, 5
 BB_ZEROS_ORIGINAL, BB_ZEROS_RESCALE, BB_ZEROS_QUANTIZED = 0, 1, 2
 BB_LAYOUT_COMPRESSED, BB_LAYOUT_INTERLEAVED_16, BB_LAYOUT_INTERLEAVED_8 = 0, 1, 2
+BB_TILE_ROW_MAJOR, BB_TILE_SLAB = 0, 1
+BB_TILE_ROWS, BB_TILE_ROW_BYTES = 32, 512
 (BB_KERNEL_AUTO, BB_KERNEL_GENERIC, BB_KERNEL_GEMV_MMA, BB_KERNEL_GEMV_I8, BB_KERNEL_GEMM_TS,
  BB_KERNEL_GEMM_TS_I8, BB_KERNEL_GEMV_STREAMK, BB_KERNEL_GEMV_SLAB) = range(8)
 
@@ -29,7 +31,7 @@ EXPORTS = [
     "bb_init", "bb_matmul", "bb_matmul_scatter", "bb_workspace_bytes", "bb_select_kernel", "bb_kernel_name", "bb_set_kernel_override",
     "bb_launch_count", "bb_last_error", "bb_version", "bb_compress_host", "bb_interleave_host",
     "bb_transform_weight_device", "bb_repack_gptq_qweight_device", "bb_repack_gptq_qzeros_device",
-    "bb_debug_decode", "bb_debug_dequant",
+    "bb_retile_weight_device", "bb_debug_decode", "bb_debug_dequant",
 ]
 
 
@@ -39,7 +41,7 @@ class MatmulDesc(ctypes.Structure):
         ("w_bits", ctypes.c_int32), ("accum_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
         ("group_size", ctypes.c_int32), ("with_scaling", ctypes.c_int32), ("with_zeros", ctypes.c_int32),
         ("zeros_mode", ctypes.c_int32), ("with_bias", ctypes.c_int32), ("w_layout", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 3),
+        ("w_tile", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2),
     ]
 
 
@@ -81,6 +83,7 @@ def load() -> ctypes.CDLL:
     lib.bb_transform_weight_device.argtypes = [vp, vp, i64, i64, i32, i32, vp]; lib.bb_transform_weight_device.restype = i32
     lib.bb_repack_gptq_qweight_device.argtypes = [vp, vp, i64, i64, i32, i32, vp]; lib.bb_repack_gptq_qweight_device.restype = i32
     lib.bb_repack_gptq_qzeros_device.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]; lib.bb_repack_gptq_qzeros_device.restype = i32
+    lib.bb_retile_weight_device.argtypes = [vp, vp, i64, i64, i32, vp]; lib.bb_retile_weight_device.restype = i32
     lib.bb_debug_decode.argtypes = [i32, i32, i32, i32, vp, vp, i32, vp]; lib.bb_debug_decode.restype = i32
     lib.bb_debug_dequant.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]; lib.bb_debug_dequant.restype = i32
     _lib = lib

@@ -63,7 +63,12 @@ static int validate(const bb_matmul_desc* d) {
   if (d->a_dtype != BB_I8 && d->out_dtype != BB_F16 && d->out_dtype != BB_BF16 && d->out_dtype != BB_F32) {
     set_error("float path supports out_dtype float16 | bfloat16 | float32"); return 1;
   }
-  if (d->reserved[0] || d->reserved[1] || d->reserved[2]) { set_error("reserved fields must be zero"); return 1; }
+  if (d->reserved[0] || d->reserved[1]) { set_error("reserved fields must be zero"); return 1; }
+  if (d->w_tile != BB_TILE_ROW_MAJOR && d->w_tile != BB_TILE_SLAB) { set_error("bad w_tile %d", d->w_tile); return 1; }
+  if (d->w_tile == BB_TILE_SLAB && !tile_shape_ok(*d)) {
+    set_error("BB_TILE_SLAB needs N %% %d == 0 and K*bits/8 %% %d == 0 (N=%d K=%d bits=%d)", BB_TILE_ROWS, BB_TILE_ROW_BYTES, d->N, d->K, d->w_bits);
+    return 1;
+  }
   if (!generic_supported(*d)) { set_error("configuration not supported (K*bits must be a multiple of 32)"); return 1; }
   return 0;
 }
@@ -81,6 +86,13 @@ static int select(const bb_matmul_desc& d, int m) {
       case BB_KERNEL_GEMV_SLAB: if (gemv_slab_supported(d, m)) return ov; break;
     }
     return -1;
+  }
+  if (d.w_tile == BB_TILE_SLAB) {
+    // slab-tiled storage is consumed by the two TMA kernels (a different tensor map, nothing else) and by the generic kernel;
+    // the register-streaming kernels address rows directly and are not offered this layout
+    if (gemv_slab_supported(d, m)) return BB_KERNEL_GEMV_SLAB;
+    if (gemm_ts_supported(d, m)) return d.a_dtype == BB_I8 ? BB_KERNEL_GEMM_TS_I8 : BB_KERNEL_GEMM_TS;
+    return BB_KERNEL_GENERIC;
   }
   // m <= 8 (one n8 MMA tile): streaming kernels; above that the tcgen05 kernel (split-K keeps the SMs busy at small m)
   // is faster (12288^2 sweep, tools/smallm_sweep.py); the streaming kernels stay as the fallback up to m = 32.

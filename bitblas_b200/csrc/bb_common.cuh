@@ -100,6 +100,16 @@ __host__ __device__ __forceinline__ int field_bitpos(int o, int bits, int layout
   return pos;
 }
 
+// BB_TILE_SLAB storage: byte `b` of packed row `n` (row_bytes per row) lives at this offset
+__host__ __device__ __forceinline__ size_t tiled_byte_offset(long long n, long long b, long long row_bytes) {
+  const long long upr = row_bytes / BB_TILE_ROW_BYTES;
+  return size_t((((n / BB_TILE_ROWS) * upr + b / BB_TILE_ROW_BYTES) * BB_TILE_ROWS + n % BB_TILE_ROWS) * BB_TILE_ROW_BYTES +
+                b % BB_TILE_ROW_BYTES);
+}
+inline bool tile_shape_ok(const bb_matmul_desc& d) {
+  return d.N % BB_TILE_ROWS == 0 && ((long long)d.K * d.w_bits / 8) % BB_TILE_ROW_BYTES == 0 && ((long long)d.K * d.w_bits) % 8 == 0;
+}
+
 // where a kernel epilogue stores C[m, n]: one local buffer, or the same element in every peer's buffer
 struct OutSpec {
   void* ptr[BB_MAX_PEERS];

@@ -78,6 +78,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -172,6 +179,7 @@ struct TsParams {
   int splits;        // split-K factor (>1: fp32 / int32 partials go to `ws`, reduced by splitk_reduce_kernel)
   int kb_per_split;  // k-blocks per split
   void* ws;          // [splits][M][N] partials
+  int w_tiled;       // BB_TILE_SLAB weight storage: tmW is the 4-D map {512 B, 32 rows, segments per row, row blocks}
   int staged_epi;    // 16-bit outputs: transpose the accumulator tile through shared memory, 16-byte row-major stores (see epilogue)
 };
 
@@ -385,7 +393,12 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kb >= S) mbar_wait(&empty[s], par);
         mbar_arrive_expect_tx(&full[s], SM::kStageBytes);
         tma_load_2d(sA + s * SM::kActBytes, &tmA, (kb0 + kb) * KB, m0, &full[s]);
-        tma_load_2d(sW + s * SM::kWBytes, &tmW, (kb0 + kb) * PRB, n0, &full[s]);
+        if (p.w_tiled) {   // the same 128 x PRB bytes, gathered from four 32-row blocks of the slab-tiled storage
+          const int byte = (kb0 + kb) * PRB;
+          tma_load_4d(sW + s * SM::kWBytes, &tmW, byte % BB_TILE_ROW_BYTES, 0, byte / BB_TILE_ROW_BYTES, n0 / BB_TILE_ROWS, &full[s]);
+        } else {
+          tma_load_2d(sW + s * SM::kWBytes, &tmW, (kb0 + kb) * PRB, n0, &full[s]);
+        }
         if (++s == S) { s = 0; par ^= 1; }
       }
     }
@@ -800,6 +813,23 @@ int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint
   return 0;
 }
 
+// BB_TILE_SLAB storage [N/32][row_bytes/512][32][512 B] as a 4-D tensor; box = {PRB bytes, 32 rows, 1 segment, 4 row blocks}
+// lands in shared memory as the same dense [128 rows][PRB] tile the row-major 2-D box produces
+int make_map_w_tiled(CUtensorMap* map, const void* base, uint64_t row_bytes, uint64_t rows, uint32_t prb) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 4; }
+  const uint64_t upr = row_bytes / BB_TILE_ROW_BYTES;
+  cuuint64_t dims[4] = {BB_TILE_ROW_BYTES, BB_TILE_ROWS, upr, rows / BB_TILE_ROWS};
+  cuuint64_t strides[3] = {BB_TILE_ROW_BYTES, uint64_t(BB_TILE_ROW_BYTES) * BB_TILE_ROWS, uint64_t(BB_TILE_ROW_BYTES) * BB_TILE_ROWS * upr};
+  cuuint32_t box[4] = {prb, BB_TILE_ROWS, 1, TS_ROWS / BB_TILE_ROWS};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (4-D, slab-tiled W) failed with CUresult %d", int(r)); return 4; }
+  return 0;
+}
+
 template <typename T, int BITS, int BM, bool IL>
 int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
   using SM = TsSmem<T, BITS, BM>;
@@ -847,8 +877,10 @@ int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
                        CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const uint64_t wrow = uint64_t(a.d.K) * BITS / 8;
-  rc = make_map_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, wrow, uint64_t(a.d.N), wrow, SM::kPRB, TS_ROWS,
-                   CU_TENSOR_MAP_SWIZZLE_NONE);
+  p.w_tiled = a.d.w_tile == BB_TILE_SLAB ? 1 : 0;
+  if (p.w_tiled) rc = make_map_w_tiled(&tmW, a.W, wrow, uint64_t(a.d.N), SM::kPRB);
+  else rc = make_map_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, wrow, uint64_t(a.d.N), wrow, SM::kPRB, TS_ROWS,
+                        CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   const int grid = tiles * p.splits;
   kernel<<<grid, TS_THREADS, smem_bytes, a.stream>>>(tmA, tmW, p);

@@ -1182,6 +1182,7 @@ size_t gemv_streamk_workspace_bytes() { return sk_workspace_bytes(); }
 
 bool gemv_mma_supported(const bb_matmul_desc& d, int m) {
   if (m < 1 || m > 32) return false;
+  if (d.w_tile != BB_TILE_ROW_MAJOR) return false;   // this kernel streams whole rows with plain loads
   if (d.a_dtype != BB_F16 && d.a_dtype != BB_BF16) return false;
   if (d.w_fmt != BB_W_UINT && d.w_fmt != BB_W_INT) return false;
   if (d.w_bits != 4 && d.w_bits != 2) return false;
@@ -1236,6 +1237,7 @@ int launch_gemv_streamk(const MatmulArgs& a) {
 
 bool gemv_i8_supported(const bb_matmul_desc& d, int m) {
   if (m < 1 || m > 32) return false;
+  if (d.w_tile != BB_TILE_ROW_MAJOR) return false;
   if (d.a_dtype != BB_I8 || d.accum_dtype != BB_I32) return false;
   if (d.w_fmt != BB_W_UINT && d.w_fmt != BB_W_INT) return false;
   if (d.w_bits != 4 && d.w_bits != 2) return false;

@@ -66,7 +66,7 @@ constexpr uint32_t GS_SUSPEND_NS = 20000;   // try_wait suspend-time hint: a wai
                                              // instead of re-issuing the probe (the default limit re-issued it ~12 times per wait: 14 %
                                              // of all issued instructions were wait-loop instructions)
 
-__host__ __device__ constexpr int gs_threads(int NG) { return (GS_GW * NG + 1 + NG / 2) * 32; }
+__host__ __device__ constexpr int gs_threads(int NG, int NF) { return (GS_GW * NG + 1 + NF) * 32; }   // consumers + issuer + finishers
 
 struct SlabParams {
   const void* A;
@@ -89,6 +89,7 @@ struct SlabParams {
   unsigned int nonce;
   int dbg;          // tuning diagnostics (BB_GS_DBG): 1 = consumers skip the arithmetic, 4 = no sums, 16 = no parameter conversion
                     // (results are wrong with any of them set)
+  const uint8_t* Wt; // BB_TILE_SLAB storage (else null): unit (rb, ku) is the contiguous 16 KB block number rb * UPR + ku
   int fast_params;  // group size 128, 8-aligned group count, N % 32 == 0, aligned pointers: 16-byte async copies of the parameters
 };
 
@@ -116,6 +117,9 @@ __device__ __forceinline__ void gs_mbar_wait(uint32_t bar, uint32_t parity) {
       "GS_DONE_%=:\n"
       "}\n" ::"r"(bar), "r"(parity), "r"(GS_SUSPEND_NS) : "memory");
 }
+// (measured and rejected: a nanosleep back-off between the helper warps' barrier probes.  The probe loops are 16 % of all issued
+//  instructions, but removing them made the kernel 1.7 % SLOWER -- the schedulers are not short of issue slots, the consumer warps
+//  are bound by their own dependent-instruction latency; profiles/r2_slab_v7_notes.txt)
 __device__ __forceinline__ void gs_tma_2d(uint32_t dst, const void* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                "l"(map), "r"(c0), "r"(c1), "r"(bar)
@@ -207,14 +211,14 @@ __device__ __forceinline__ int gs_range_begin(int ri, int T, int R) { return int
 // NG consumer groups per CTA, MINB CTAs per SM: (2, 2) or (4, 1).  SC = ring depth as a compile-time constant (0: p.stages at run
 // time, the tuning / test variant): with a constant depth every stage address is base + immediate -- the run-time variant spends
 // ~40 integer instructions per unit and warp re-deriving the region bases (profiles/r2_gemv_slab_ncu_full.txt, SASS page)
-template <typename T, bool IL, int NG, int MINB, int SC>
-__global__ void __launch_bounds__(gs_threads(NG), MINB)
+// NF = finisher warps (S % NF == 0; finisher f serves the units i = f (mod NF) of the range)
+template <typename T, bool IL, int NG, int MINB, int SC, int NF>
+__global__ void __launch_bounds__(gs_threads(NG, NF), MINB)
 gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   constexpr bool F16 = std::is_same<T, __half>::value;
   constexpr bool HI = F16;   // odd nibbles decoded in place (mantissa bits 4..7 under exponent 2^6: exactly 64 + u)
   constexpr uint32_t MAGIC = TypeTraits<T>::kMagic;
   constexpr uint32_t MAGIC_HI = 0x54005400u;
-  constexpr int NF = NG / 2;                 // finisher warps
   constexpr int NCW = GS_GW * NG;            // consumer warps
   extern __shared__ uint8_t gs_raw[];
   const int S = SC > 0 ? SC : p.stages;
@@ -268,7 +272,8 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
     // one weight TMA box {128 x u32 = 512 B, 32 rows} -> dense [32][512 B] (rows past N / columns past K/2 are zero-filled and
     // never stored / consumed; the transaction count is always the full box), the activation slab, the raw parameters
     auto unit_w = [&](int rb, int ku, int slot) {   // lane 0
-      gs_tma_2d(Wb + uint32_t(slot) * GS_WBYTES, &tmW, ku * (GS_ROW_BYTES / 4), rb * GS_ROWS, Bb + 8u * slot);
+      if (p.Wt) gs_bulk_g2s(Wb + uint32_t(slot) * GS_WBYTES, p.Wt + (size_t(rb) * UPR + ku) * GS_WBYTES, GS_WBYTES, Bb + 8u * slot);
+      else gs_tma_2d(Wb + uint32_t(slot) * GS_WBYTES, &tmW, ku * (GS_ROW_BYTES / 4), rb * GS_ROWS, Bb + 8u * slot);
     };
     auto unit_params = [&](int rb, int ku, int slot) {   // all 32 lanes: lane = row of the unit
       const uint32_t bar = Bb + 8u * (2 * S + slot);
@@ -685,9 +690,9 @@ int gs_occupancy(KernelT k, int variant, int threads, int smem, int dev) {
   // per (kernel variant, device): opt-in shared memory once (the device maximum); per dynamic size: occupancy, cached
   struct Entry { int smem, occ; };
   static std::mutex mu;
-  static Entry cache[16][GS_MAX_DEVICES][8];
-  static int used[16][GS_MAX_DEVICES];
-  static bool attr[16][GS_MAX_DEVICES];
+  static Entry cache[24][GS_MAX_DEVICES][8];
+  static int used[24][GS_MAX_DEVICES];
+  static bool attr[24][GS_MAX_DEVICES];
   static bool init = false;
   std::lock_guard<std::mutex> lk(mu);
   if (!init) { memset(cache, 0, sizeof(cache)); memset(used, 0, sizeof(used)); memset(attr, 0, sizeof(attr)); init = true; }
@@ -720,6 +725,7 @@ bool gemv_slab_supported(const bb_matmul_desc& d, int m) {
   if (d.w_bits != 4) return false;
   if (d.w_layout == BB_LAYOUT_INTERLEAVED_8) return false;
   if (d.N % 16 || d.K % 256) return false;
+  if (d.w_tile == BB_TILE_SLAB && (d.N % GS_ROWS || d.K % GS_KU)) return false;   // whole units only
   const int g = d.group_size <= 0 ? d.K : d.group_size;
   if (g % 128 || d.K % g) return false;
   if (d.with_zeros && !d.with_scaling) return false;
@@ -743,6 +749,7 @@ int launch_gemv_slab(const MatmulArgs& a) {
   const int dev = current_device();
   // consumer groups per CTA x CTAs per SM: (4, 1) shares one deep ring between four groups, (2, 2) runs two CTAs per SM
   const int ng = env_int("BB_GS_NG", 2) == 4 ? 4 : 2;
+  const int nf = env_int("BB_GS_NF", 1) == 2 ? 2 : 1;   // finisher warps of the (2 groups, 4 stages) configuration
   SlabParams p;
   p.A = a.A; p.scale = d.with_scaling ? a.scale : nullptr; p.zeros = d.with_zeros ? a.zeros : nullptr;
   p.bias = d.with_bias ? a.bias : nullptr; p.out = make_outspec(a);
@@ -761,7 +768,12 @@ int launch_gemv_slab(const MatmulArgs& a) {
   p.stages = stages;
   p.dbg = env_int("BB_GS_DBG", 0);
   CUtensorMap tm;
-  if (!get_w_map(&tm, a.W, d.N, d.K)) { set_error("gemv_slab: cuTensorMapEncodeTiled failed"); return 4; }
+  p.Wt = nullptr;
+  if (d.w_tile == BB_TILE_SLAB) {
+    // slab-tiled storage: a unit is one contiguous 16 KB block -- a single bulk copy, no tensor map
+    p.Wt = reinterpret_cast<const uint8_t*>(a.W);
+    memset(&tm, 0, sizeof(tm));
+  } else if (!get_w_map(&tm, a.W, d.N, d.K)) { set_error("gemv_slab: cuTensorMapEncodeTiled failed"); return 4; }
   p.fast_params = (p.g128 == 1 && (p.G & 7) == 0 && (d.N % GS_ROWS) == 0 &&
                    (!d.with_scaling || (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0) &&
                    (!d.with_zeros || (reinterpret_cast<uintptr_t>(a.zeros) & 15) == 0)) ? 1 : 0;
@@ -775,15 +787,15 @@ int launch_gemv_slab(const MatmulArgs& a) {
   const int sms = device_sm_count();
   static const bool pdl = [] { const char* e = getenv("BB_PDL"); return e ? atoi(e) != 0 : true; }();
 
-#define BB_GS_GO(TT, ILV, NGV, MINBV, SCV, VAR)                                                        \
+#define BB_GS_GO(TT, ILV, NGV, MINBV, SCV, NFV, VAR)                                                   \
   {                                                                                                    \
-    auto k = gemv_slab_kernel<TT, ILV, NGV, MINBV, SCV>;                                               \
-    int occ = gs_occupancy(k, VAR, gs_threads(NGV), smem, dev);                                        \
+    auto k = gemv_slab_kernel<TT, ILV, NGV, MINBV, SCV, NFV>;                                          \
+    int occ = gs_occupancy(k, VAR, gs_threads(NGV, NFV), smem, dev);                                   \
     if (occ < 0) { set_error("gemv_slab: kernel does not fit on this device (stages=%d)", stages); return 4; } \
     occ = std::min(occ, MINBV);                                                                        \
     const int grid = std::max(1, std::min(p.T, occ * sms));                                            \
     cudaLaunchConfig_t cfg = {};                                                                       \
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gs_threads(NGV));                                    \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gs_threads(NGV, NFV));                               \
     cfg.dynamicSmemBytes = smem; cfg.stream = a.stream;                                                \
     cudaLaunchAttribute attr[1];                                                                       \
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                   \
@@ -793,12 +805,13 @@ int launch_gemv_slab(const MatmulArgs& a) {
   }
   // the shipped configuration (2 groups, 4 stages) has the ring depth compiled in; every other knob setting runs the run-time-depth
   // variants (tuning sweeps, tests of the ring logic)
-#define BB_GS_NG(TT, ILV, VB)                                    \
-  if (ng == 4) BB_GS_GO(TT, ILV, 4, 1, 0, VB + 0)                \
-  else if (stages == 4) BB_GS_GO(TT, ILV, 2, 2, 4, VB + 1)       \
-  else BB_GS_GO(TT, ILV, 2, 2, 0, VB + 2)
-  if (f16) { if (il) { BB_GS_NG(__half, true, 0) } else { BB_GS_NG(__half, false, 3) } }
-  else { if (il) { BB_GS_NG(__nv_bfloat16, true, 6) } else { BB_GS_NG(__nv_bfloat16, false, 9) } }
+#define BB_GS_NG(TT, ILV, VB)                                                  \
+  if (ng == 4) BB_GS_GO(TT, ILV, 4, 1, 0, 2, VB + 0)                           \
+  else if (stages == 4 && nf == 2) BB_GS_GO(TT, ILV, 2, 2, 4, 2, VB + 1)       \
+  else if (stages == 4) BB_GS_GO(TT, ILV, 2, 2, 4, 1, VB + 2)                  \
+  else BB_GS_GO(TT, ILV, 2, 2, 0, 1, VB + 3)
+  if (f16) { if (il) { BB_GS_NG(__half, true, 0) } else { BB_GS_NG(__half, false, 4) } }
+  else { if (il) { BB_GS_NG(__nv_bfloat16, true, 8) } else { BB_GS_NG(__nv_bfloat16, false, 12) } }
 #undef BB_GS_NG
 #undef BB_GS_GO
   BB_LAUNCH_CHECK();

@@ -15,10 +15,15 @@ namespace {
 constexpr int MT = 4;          // rows of A per warp pass
 constexpr int WARPS = 8;       // warps (= output columns) per block
 
-__device__ __forceinline__ uint32_t load_field(const uint8_t* __restrict__ Wrow, int k, int bits, int layout) {
-  if (bits == 8) return Wrow[k];
+// Wrow: row-major storage -> the row's first byte; BB_TILE_SLAB storage -> the first byte of the row's first 512-byte segment
+// (segments of one row are then 32 x 512 bytes apart)
+__device__ __forceinline__ uint32_t load_field(const uint8_t* __restrict__ Wrow, int k, int bits, int layout, int tiled) {
+  auto at = [&](size_t b) -> size_t {
+    return tiled ? (b / BB_TILE_ROW_BYTES) * (size_t(BB_TILE_ROWS) * BB_TILE_ROW_BYTES) + b % BB_TILE_ROW_BYTES : b;
+  };
+  if (bits == 8) return Wrow[at(size_t(k))];
   const int epw = 32 / bits;
-  const uint32_t word = reinterpret_cast<const uint32_t*>(Wrow)[k / epw];
+  const uint32_t word = *reinterpret_cast<const uint32_t*>(Wrow + at(size_t(k / epw) * 4));
   const int pos = field_bitpos(k % epw, bits, layout);
   return (word >> pos) & ((1u << bits) - 1u);
 }
@@ -115,7 +120,8 @@ generic_float_kernel(const bb_matmul_desc d, const T* __restrict__ A, const uint
   const int g = d.group_size <= 0 ? K : d.group_size;
   const int G = K / g;
   const size_t row_bytes = size_t(K) * bits / 8;
-  const uint8_t* Wrow = W + size_t(n) * row_bytes;
+  const int tiled = d.w_tile == BB_TILE_SLAB;
+  const uint8_t* Wrow = W + (tiled ? tiled_byte_offset(n, 0, (long long)row_bytes) : size_t(n) * row_bytes);
   const bool use_fma = d.w_layout != BB_LAYOUT_COMPRESSED && (d.w_fmt == BB_W_UINT || d.w_fmt == BB_W_INT) &&
                        std::is_same<T, __half>::value;
   float acc[MT];
@@ -123,7 +129,7 @@ generic_float_kernel(const bb_matmul_desc d, const T* __restrict__ A, const uint
   for (int i = 0; i < MT; ++i) acc[i] = 0.f;
 
   for (int k = lane; k < K; k += 32) {
-    const uint32_t u = load_field(Wrow, k, bits, d.w_layout);
+    const uint32_t u = load_field(Wrow, k, bits, d.w_layout, tiled);
     const int gi = k / g;
     T w;
     if (d.with_zeros && d.zeros_mode == BB_ZEROS_QUANTIZED) {
@@ -175,12 +181,13 @@ generic_int_kernel(const bb_matmul_desc d, const int8_t* __restrict__ A, const u
   const int K = d.K, bits = d.w_bits;
   const int g = d.group_size <= 0 ? K : d.group_size;
   const int G = K / g;
-  const uint8_t* Wrow = W + size_t(n) * (size_t(K) * bits / 8);
+  const int tiled = d.w_tile == BB_TILE_SLAB;
+  const uint8_t* Wrow = W + (tiled ? tiled_byte_offset(n, 0, (long long)K * bits / 8) : size_t(n) * (size_t(K) * bits / 8));
   int acc[MT];
 #pragma unroll
   for (int i = 0; i < MT; ++i) acc[i] = 0;
   for (int k = lane; k < K; k += 32) {
-    const uint32_t u = load_field(Wrow, k, bits, d.w_layout);
+    const uint32_t u = load_field(Wrow, k, bits, d.w_layout, tiled);
     const int gi = k / g;
     int w;
     if (d.with_zeros && d.zeros_mode == BB_ZEROS_QUANTIZED) {

@@ -165,6 +165,17 @@ int layout_from_target(int target_bits) {
 
 using namespace bb;
 
+// BB_TILE_SLAB re-tiling: one 16-byte chunk per thread; consecutive threads walk the ROW-MAJOR side (coalesced reads going in,
+// coalesced writes coming back), the tiled side is contiguous per 512-byte segment
+static __global__ void retile_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows, int64_t row_bytes, int inverse) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t cpr = row_bytes / 16;
+  if (i >= rows * cpr) return;
+  const int64_t n = i / cpr, b = (i - n * cpr) * 16;
+  const size_t t = tiled_byte_offset(n, b, row_bytes) / 16;
+  if (inverse) out[i] = in[t]; else out[t] = in[i];
+}
+
 extern "C" {
 
 int bb_compress_host(const int8_t* in, int8_t* out, int64_t rows, int64_t cols, int bits) {
@@ -211,6 +222,20 @@ int bb_transform_weight_device(const int8_t* w, int8_t* out, int64_t rows, int64
   const int threads = 256;
   transform_weight_kernel<<<(unsigned)((nwords + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
       w, reinterpret_cast<uint32_t*>(out), rows, cols, bits, layout_from_target(target_bits));
+  BB_LAUNCH_CHECK();
+  return 0;
+}
+
+int bb_retile_weight_device(const int8_t* in, int8_t* out, int64_t rows, int64_t row_bytes, int inverse, void* stream) {
+  if (!in || !out || in == out || rows <= 0 || row_bytes <= 0 || rows % BB_TILE_ROWS || row_bytes % BB_TILE_ROW_BYTES ||
+      (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
+    set_error("bb_retile_weight_device: needs distinct 16-byte aligned buffers, rows %% %d == 0, row_bytes %% %d == 0", BB_TILE_ROWS, BB_TILE_ROW_BYTES);
+    return 1;
+  }
+  const int64_t chunks = rows * (row_bytes / 16);
+  const int threads = 256;
+  retile_kernel<<<(unsigned)((chunks + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), rows, row_bytes, inverse);
   BB_LAUNCH_CHECK();
   return 0;
 }

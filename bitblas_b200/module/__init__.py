@@ -207,7 +207,7 @@ class Linear(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(lib.bb_repack_gptq_qweight_device(qw.data_ptr(), out.data_ptr(), K, N, bits, tgt, stream),
                        "bb_repack_gptq_qweight_device")
-            self.qweight = out
+            self.qweight = op.tile_weight(out) if op.weight_tiled else out   # propagate_b: slab tiling of the packed rows
             self.scales = gptq_module.scales.to(dev).T.contiguous().view(self.torch_dtype)
             qz = gptq_module.qzeros.to(dev).contiguous().view(torch.int32)  # [K/g, N*bits/32]
             G = K // self.group_size

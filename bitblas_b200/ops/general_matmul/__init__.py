@@ -97,15 +97,24 @@ class MatmulConfig(OperatorConfig):
         self._set("M", tuple(self.M) if isinstance(self.M, list) else self.M)
         if isinstance(self.optimize_stratety, int) and not isinstance(self.optimize_stratety, OptimizeStrategy):
             self._set("optimize_stratety", OptimizeStrategy(self.optimize_stratety))
-        # The ladder (mma.sync fragment-ordered) weight/input propagation of the reference
-        # (general_matmul/__init__.py:113-157) has no meaning for tcgen05/TMA operands: the B200 kernels consume the
-        # plain [N, K*bits/8] storage directly, so both flags legalise to NonTransform.  A request for a transform is
-        # accepted (for API compatibility) and recorded, but the storage layout stays un-propagated.
+        # Weight propagation (general_matmul/__init__.py:113-157).  The reference re-tiles W offline into mma.sync /
+        # ldmatrix fragment order; tcgen05 operands are laid out in TMEM by the kernels themselves, so that particular
+        # permutation has no meaning here.  What an offline layout still buys on B200 is DRAM / TMA locality: a requested
+        # propagate_b selects the slab tiling BB_TILE_SLAB (include/bitblas_b200.h: [N/32][row_bytes/512][32][512 B]; one
+        # work unit of the decode GEMV = one contiguous 16 KB block).  Default (None / False): the reference's row-major
+        # storage, byte-compatible with its checkpoints.  propagate_a never applies (activations are consumed as they are).
         requested_b = self._legalize_propagate(self.propagate_b)
-        if requested_b not in (None, TransformKind.NonTransform):
-            logger.warning("propagate_b=%s is an mma.sync layout and is ignored on B200", requested_b)
+        want_tile = requested_b not in (None, TransformKind.NonTransform)
+        if want_tile:
+            wbits = {"int4": 4, "uint4": 4, "int2": 2, "uint2": 2}.get(self.W_dtype)
+            ok = (wbits is not None and self.W_dtype != self.A_dtype and self.N % 128 == 0
+                  and (self.K * wbits // 8) % _lib.BB_TILE_ROW_BYTES == 0 and (self.K * wbits) % 8 == 0)
+            if not ok:
+                logger.warning("propagate_b: slab tiling needs a 4/2-bit integer weight, N %% 128 == 0 and K*bits/8 %% 512 == 0 "
+                               "(N=%s K=%s W_dtype=%s); keeping the row-major storage", self.N, self.K, self.W_dtype)
+                want_tile = False
         self._set("propagate_a", TransformKind.NonTransform)
-        self._set("propagate_b", TransformKind.NonTransform)
+        self._set("propagate_b", TransformKind.LDMatrixTransform if want_tile else TransformKind.NonTransform)
         if self.zeros_mode is None:
             self._set("zeros_mode", "original")
         self._initialize_fast_decoding(self.fast_decoding)
@@ -307,7 +316,35 @@ class Matmul(Operator):
             d.w_layout = _lib.BB_LAYOUT_INTERLEAVED_8 if c.A_dtype == "int8" else _lib.BB_LAYOUT_INTERLEAVED_16
         else:
             d.w_layout = _lib.BB_LAYOUT_COMPRESSED
+        d.w_tile = _lib.BB_TILE_SLAB if self.weight_tiled else _lib.BB_TILE_ROW_MAJOR
         return d
+
+    @property
+    def weight_tiled(self) -> bool:
+        """stored weight is in the slab tiling (MatmulConfig.propagate_b)"""
+        return self.config.propagate_b != TransformKind.NonTransform
+
+    def tile_weight(self, w: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+        """row-major packed storage [N, K*bits/8] <-> BB_TILE_SLAB (same shape and bytes, 512-byte row segments re-ordered as
+        [N/32][row_bytes/512][32][512]).  CUDA tensors: bb_retile_weight_device; CPU tensors: a torch permute."""
+        R, B = _lib.BB_TILE_ROWS, _lib.BB_TILE_ROW_BYTES
+        w = w.contiguous()
+        n, rb = w.shape[0], w.shape[1] * w.element_size()
+        if n % R or rb % B:
+            raise ValueError(f"slab tiling needs rows % {R} == 0 and row bytes % {B} == 0 (got {n} x {rb})")
+        if w.is_cuda:
+            out = torch.empty_like(w)
+            _lib.ensure_init(w.device.index or 0)
+            with torch.cuda.device(w.device):
+                _lib.check(_lib.load().bb_retile_weight_device(w.data_ptr(), out.data_ptr(), n, rb, int(inverse),
+                                                               torch.cuda.current_stream(w.device).cuda_stream), "bb_retile_weight_device")
+            return out
+        b = w.view(torch.int8).reshape(n, rb)
+        if inverse:
+            t = b.reshape(n // R, rb // B, R, B).permute(0, 2, 1, 3)
+        else:
+            t = b.reshape(n // R, R, rb // B, B).permute(0, 2, 1, 3)
+        return t.contiguous().reshape(n, rb).view(w.dtype).reshape(w.shape)
 
     # ---- weight / input preparation -------------------------------------------------------------
     def retrieve_weight_shape(self):
@@ -332,6 +369,8 @@ class Matmul(Operator):
             weight = weight.char()
         if self.weight_transform is not None:
             weight = self.weight_transform(weight).contiguous()
+        if self.weight_tiled:
+            weight = self.tile_weight(weight)
         return weight
 
     def transform_input(self, input_tensor):

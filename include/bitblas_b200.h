@@ -62,6 +62,21 @@ typedef enum bb_wlayout {
   BB_LAYOUT_INTERLEAVED_8 = 2    /* + LOP3 interleave,  8-bit target (A_dtype == int8)               */
 } bb_wlayout;
 
+/* Offline tiling of the packed weight matrix (MatmulConfig.propagate_b).  The reference's weight propagation re-tiles W offline
+ * so that its mma.sync kernels can use ldmatrix-friendly, conflict-free tiles (bitblas/ops/ladder_permutate/
+ * ladder_permutate_impl.py:12-116, bitblas/gpu/matmul_analysis.py:691-801, general_matmul/__init__.py:113-157).  On B200 the
+ * tensor-core operand layout is produced in TMEM by the kernels themselves; what an offline layout can still buy is DRAM/TMA
+ * locality.  BB_TILE_SLAB stores the packed rows as [N/32][row_bytes/512][32 rows][512 B] (row_bytes = K*bits/8): one 16 KB
+ * work unit of the decode GEMV is ONE contiguous block, and the 128-row x k-block tile of the tcgen05 kernel is four 4-D TMA
+ * box rows of it.  Same bytes, same size, same interleave inside each 32-bit word; only the order of 512-byte row segments
+ * changes.  Needs N % 32 == 0 and row_bytes % 512 == 0. */
+typedef enum bb_wtile {
+  BB_TILE_ROW_MAJOR = 0,
+  BB_TILE_SLAB = 1
+} bb_wtile;
+#define BB_TILE_ROWS 32
+#define BB_TILE_ROW_BYTES 512
+
 /* One matmul problem family: C[m, N] = A[m, K] x dequant(W[N, K])^T (+ bias).  Mirrors the fields of
  * MatmulConfig that reach the kernel (general_matmul/__init__.py:58-95); `layout` is always "nt"
  * (tirscript/matmul_dequantize_impl.py:912-915). */
@@ -79,7 +94,8 @@ typedef struct bb_matmul_desc {
   int32_t zeros_mode;   /* bb_zeros_mode                                              */
   int32_t with_bias;    /* Bias[N] in out_dtype-compatible A_dtype                    */
   int32_t w_layout;     /* bb_wlayout                                                 */
-  int32_t reserved[3];  /* must be 0                                                  */
+  int32_t w_tile;       /* enum bb_wtile, from MatmulConfig.propagate_b; 0 = the reference row-major storage */
+  int32_t reserved[2];  /* must be 0                                                  */
 } bb_matmul_desc;
 
 /* kernel families the dispatcher can choose (introspection / tests) */
@@ -158,6 +174,10 @@ int bb_repack_gptq_qweight_device(const int32_t* qweight_gptq, int8_t* out, int6
  * (mode quantized).  scales is [N, K/g] in a_dtype (already transposed). */
 int bb_repack_gptq_qzeros_device(const int32_t* qzeros_gptq, const void* scales, void* zeros_out, int64_t groups,
                                  int64_t N, int bits, int zeros_mode, int a_dtype, int v2, void* stream);
+
+/* device: BB_TILE_SLAB re-tiling of a stored weight matrix (either layout of bb_wlayout): in[rows, row_bytes] row-major ->
+ * out as [rows/32][row_bytes/512][32][512] (inverse != 0: back to row-major).  in != out.  rows % 32 == 0, row_bytes % 512 == 0. */
+int bb_retile_weight_device(const int8_t* in, int8_t* out, int64_t rows, int64_t row_bytes, int inverse, void* stream);
 
 /* ---- test hook: run the library's own in-register decode over an array of packed words (device ptrs).
  * kind: 0 = to f16 (8 values / group), 1 = to bf16, 2 = to int8 (16 values / group).  Used by the GPU KATs

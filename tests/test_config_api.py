@@ -147,3 +147,31 @@ def test_bitblas_alias_package():
     assert bb.Matmul is bitblas.Matmul and bb.__version__ == "0.1.0"
     assert global_operator_cache.size() >= 0 and isinstance(get_database_path(), str)
     bb.set_log_level("INFO")
+
+
+def test_propagate_b_selects_slab_tiling():
+    """MatmulConfig(propagate_b=True): the B200 meaning of weight propagation is the slab tiling (include/bitblas_b200.h,
+    enum bb_wtile); shapes / formats it does not cover legalise back to the row-major storage like the reference's
+    __initialize_propagate does for its own unsupported cases (general_matmul/__init__.py:113-157)."""
+    import numpy as np
+    import torch
+    import bitblas_oracle as O
+    from bitblas_b200 import Matmul, MatmulConfig
+    from bitblas_b200.ops.operator import TransformKind
+    c = MatmulConfig(M=1, N=256, K=2048, A_dtype="float16", W_dtype="uint4", group_size=128, with_scaling=True, propagate_b=True)
+    assert c.propagate_b == TransformKind.LDMatrixTransform and c.propagate_a == TransformKind.NonTransform
+    assert MatmulConfig(M=1, N=256, K=2048, A_dtype="float16", W_dtype="uint4").propagate_b == TransformKind.NonTransform
+    assert MatmulConfig(M=1, N=48, K=2048, A_dtype="float16", W_dtype="uint4", propagate_b=True).propagate_b == TransformKind.NonTransform
+    assert MatmulConfig(M=1, N=256, K=512, A_dtype="float16", W_dtype="uint4", propagate_b=True).propagate_b == TransformKind.NonTransform
+    assert MatmulConfig(M=1, N=256, K=2048, A_dtype="float16", W_dtype="nf4", propagate_b=True).propagate_b == TransformKind.NonTransform
+    op, op0 = Matmul(c, enable_tuning=False), Matmul(MatmulConfig(M=1, N=256, K=2048, A_dtype="float16", W_dtype="uint4", group_size=128,
+                                                                  with_scaling=True), enable_tuning=False)
+    assert op.weight_tiled and not op0.weight_tiled and op._desc.w_tile == 1 and op0._desc.w_tile == 0
+    assert op.retrieve_weight_shape() == op0.retrieve_weight_shape()
+    g = torch.Generator().manual_seed(0)
+    fields = torch.randint(0, 16, (256, 2048), generator=g, dtype=torch.int8)
+    plain, tiled = op0.transform_weight(fields), op.transform_weight(fields)
+    assert np.array_equal(tiled.numpy(), O.slab_tile(plain.numpy()))
+    assert torch.equal(op.tile_weight(tiled, inverse=True), plain)
+    # dispatch: the decode kernel and the tcgen05 kernel take the tiled storage, the register-streaming kernels do not
+    assert op.kernel_for(1) == "gemv_slab" and op.kernel_for(4) == "gemm_ts_tcgen05" and op.kernel_for(512) == "gemm_ts_tcgen05"

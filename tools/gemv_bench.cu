@@ -2,7 +2,7 @@
 // dequantise+dot, then back-to-back timing over rotating weight copies (cold L2), for a list of shapes and tuning knobs.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/gemv_bench tools/gemv_bench.cu \
 //        -Lbitblas_b200/lib -lbitblas_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../bitblas_b200/lib'
-//   tools/gemv_bench [--kernel ID] [--iters N] [--cfg STAGES,GROUPS]... [--nocheck] NxK [NxK ...]
+//   tools/gemv_bench [--kernel ID] [--iters N] [--cfg STAGES,GROUPS[,FINISHERS]]... [--tile] [--nocheck] NxK [NxK ...]
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -20,11 +20,11 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 #define BB(x) do { int rc = (x); if (rc) { printf("bb error %d at line %d: %s\n", rc, __LINE__, bb_last_error()); exit(1);} } while (0)
 
-struct Cfg { int stages, ng; };
+struct Cfg { int stages, ng, nf; };
 
 int main(int argc, char** argv) {
   int kernel = BB_KERNEL_AUTO, iters = 200;
-  bool check = true;
+  bool check = true, tile = false;   // --tile: BB_TILE_SLAB weight storage (MatmulConfig.propagate_b)
   std::vector<Cfg> cfgs;
   std::vector<std::pair<int, int>> shapes;
   for (int i = 1; i < argc; ++i) {
@@ -32,11 +32,12 @@ int main(int argc, char** argv) {
     if (a == "--kernel") kernel = atoi(argv[++i]);
     else if (a == "--iters") iters = atoi(argv[++i]);
     else if (a == "--nocheck") check = false;
-    else if (a == "--cfg") { Cfg c{4, 2}; sscanf(argv[++i], "%d,%d", &c.stages, &c.ng); cfgs.push_back(c); }
+    else if (a == "--cfg") { Cfg c{4, 2, 1}; sscanf(argv[++i], "%d,%d,%d", &c.stages, &c.ng, &c.nf); cfgs.push_back(c); }
+    else if (a == "--tile") tile = true;
     else { int n, k; if (sscanf(a.c_str(), "%dx%d", &n, &k) == 2) shapes.push_back({n, k}); }
   }
   if (shapes.empty()) shapes.push_back({12288, 12288});
-  if (cfgs.empty()) cfgs.push_back(Cfg{4, 2});
+  if (cfgs.empty()) cfgs.push_back(Cfg{4, 2, 1});
   BB(bb_init(0));
   bb_set_kernel_override(kernel);
   cudaStream_t st; CK(cudaStreamCreate(&st));
@@ -50,6 +51,7 @@ int main(int argc, char** argv) {
     d.N = N; d.K = K; d.a_dtype = BB_F16; d.w_fmt = BB_W_UINT; d.w_bits = 4; d.accum_dtype = BB_F32; d.out_dtype = BB_F16;
     d.group_size = g; d.with_scaling = 1; d.with_zeros = 1; d.zeros_mode = BB_ZEROS_QUANTIZED; d.with_bias = 0;
     d.w_layout = BB_LAYOUT_INTERLEAVED_16;
+    d.w_tile = tile ? BB_TILE_SLAB : BB_TILE_ROW_MAJOR;
     std::mt19937 rng(1234);
     std::vector<uint32_t> hW(wbytes / 4);
     for (auto& v : hW) v = rng();
@@ -60,7 +62,16 @@ int main(int argc, char** argv) {
     for (auto& v : hA) v = __float2half(ua(rng));
     for (auto& v : hZ) v = uint8_t(rng());
     std::vector<uint8_t*> dW(copies);
-    for (int c = 0; c < copies; ++c) { CK(cudaMalloc(&dW[c], wbytes)); CK(cudaMemcpy(dW[c], hW.data(), wbytes, cudaMemcpyHostToDevice)); }
+    for (int c = 0; c < copies; ++c) {
+      CK(cudaMalloc(&dW[c], wbytes));
+      if (tile) {   // upload row-major, re-tile on the device with the library's own kernel
+        uint8_t* tmp; CK(cudaMalloc(&tmp, wbytes)); CK(cudaMemcpy(tmp, hW.data(), wbytes, cudaMemcpyHostToDevice));
+        BB(bb_retile_weight_device(reinterpret_cast<const int8_t*>(tmp), reinterpret_cast<int8_t*>(dW[c]), N, K / 2, 0, nullptr));
+        CK(cudaDeviceSynchronize()); CK(cudaFree(tmp));
+      } else {
+        CK(cudaMemcpy(dW[c], hW.data(), wbytes, cudaMemcpyHostToDevice));
+      }
+    }
     __half *dS, *dA, *dC; uint8_t* dZ; void* ws;
     CK(cudaMalloc(&dS, hS.size() * 2)); CK(cudaMemcpy(dS, hS.data(), hS.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dA, K * 2)); CK(cudaMemcpy(dA, hA.data(), K * 2, cudaMemcpyHostToDevice));
@@ -99,6 +110,7 @@ int main(int argc, char** argv) {
       char buf[32];
       snprintf(buf, 32, "%d", c.stages); setenv("BB_GS_STAGES", buf, 1);
       snprintf(buf, 32, "%d", c.ng); setenv("BB_GS_NG", buf, 1);
+      snprintf(buf, 32, "%d", c.nf); setenv("BB_GS_NF", buf, 1);
       double maxerr = -1, maxref = 0;
       if (check) {
         CK(cudaMemset(dC, 0xff, N * 2));
@@ -128,8 +140,8 @@ int main(int argc, char** argv) {
         best = std::min(best, ms / iters); sum += ms / iters;
       }
       const double us_best = best * 1e3, us_mean = sum / reps * 1e3;
-      printf("N=%d K=%d kernel=%s stages=%d groups=%d : %.2f us best %.2f us mean  %.0f GB/s  frac(6576)=%.3f  maxerr=%.3g (max|ref|=%.3g)\n",
-             N, K, bb_kernel_name(kid), c.stages, c.ng, us_best, us_mean, alg / (us_mean * 1e-6) / 1e9,
+      printf("N=%d K=%d kernel=%s%s stages=%d groups=%d finishers=%d : %.2f us best %.2f us mean  %.0f GB/s  frac(6576)=%.3f  maxerr=%.3g (max|ref|=%.3g)\n",
+             N, K, bb_kernel_name(kid), tile ? " (slab-tiled W)" : "", c.stages, c.ng, c.nf, us_best, us_mean, alg / (us_mean * 1e-6) / 1e9,
              alg / (us_mean * 1e-6) / 1e9 / 6576.1, maxerr, maxref);
       fflush(stdout);
     }
