@@ -445,6 +445,9 @@ def main():
             h_.barrier(channel=0)
             torch.cuda.synchronize()
             fused["on"] = True
+            if os.environ.get("BB_BENCH_PEER_BARRIER", "1") != "0":
+                from bitblas_b200.parallel import PeerBarrier
+                fused["barrier"] = PeerBarrier(dev)      # bb_peer_barrier: the library's own one-kernel barrier
         except Exception as ex:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable ({ex}); using NCCL all-gather", file=sys.stderr)
@@ -463,6 +466,8 @@ def main():
                                ldc=N_full, col_offset=rank * (N_full // world))
             if defer is not None:
                 defer.append(hdl)
+            elif fused.get("barrier") is not None:
+                fused["barrier"]()
             else:
                 hdl.barrier(channel=0)
             return buf
@@ -501,8 +506,11 @@ def main():
         pending = [] if (world > 1 and fused["on"] and step_sync) else None
         for op, prm, A, out, N, K in ops_c:
             run_sharded(op, prm, A, out, 1, N, defer=pending)
-        if pending:
-            pending[-1].barrier(channel=0)   # peer stores of all four projections precede it in stream order on every rank
+        if pending:   # peer stores of all four projections precede the barrier in stream order on every rank
+            if fused.get("barrier") is not None:
+                fused["barrier"]()
+            else:
+                pending[-1].barrier(channel=0)
 
     # The step is captured once per parameter set in a CUDA graph (four launches with their programmatic-dependent-launch
     # edges + the device barrier) and replayed: at 8 GPUs a shard's kernel takes a few microseconds, the four Python calls that
@@ -694,7 +702,8 @@ def main():
                             "note": f"CPU time for a 1/{wl.sample_div} row sample of the step / (GPU step time / {wl.sample_div})"}
 
     if rank == 0:
-        par = (f"column-parallel x{world}, " + (("fused peer-store epilogue over NVLink (bb_matmul_scatter) + one device barrier per "
+        par = (f"column-parallel x{world}, " + (("fused peer-store epilogue over NVLink (bb_matmul_scatter) + one device barrier ("
+               + ("bb_peer_barrier" if fused.get("barrier") is not None else "symmetric-memory library barrier") + ") per "
                + ("step" if step_sync else "projection")) if fused["on"] else "NCCL all-gather")) if world > 1 else "single GPU"
         line = {"metric": "w4a16_gemv_gbps_llama70b", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,

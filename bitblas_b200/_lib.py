@@ -19,6 +19,7 @@ BB_ZEROS_ORIGINAL, BB_ZEROS_RESCALE, BB_ZEROS_QUANTIZED = 0, 1, 2
 BB_LAYOUT_COMPRESSED, BB_LAYOUT_INTERLEAVED_16, BB_LAYOUT_INTERLEAVED_8 = 0, 1, 2
 BB_TILE_ROW_MAJOR, BB_TILE_SLAB = 0, 1
 BB_TILE_ROWS, BB_TILE_ROW_BYTES = 32, 512
+BB_PEER_FLAG_BYTES = 128
 (BB_KERNEL_AUTO, BB_KERNEL_GENERIC, BB_KERNEL_GEMV_MMA, BB_KERNEL_GEMV_I8, BB_KERNEL_GEMM_TS,
  BB_KERNEL_GEMM_TS_I8, BB_KERNEL_GEMV_STREAMK, BB_KERNEL_GEMV_SLAB) = range(8)
 
@@ -28,7 +29,7 @@ WFMT_IDS = {"uint": BB_W_UINT, "int": BB_W_INT, "nf": BB_W_NF, "fp": BB_W_FP4, "
 ZEROS_IDS = {"original": BB_ZEROS_ORIGINAL, "rescale": BB_ZEROS_RESCALE, "quantized": BB_ZEROS_QUANTIZED}
 
 EXPORTS = [
-    "bb_init", "bb_matmul", "bb_matmul_scatter", "bb_workspace_bytes", "bb_select_kernel", "bb_kernel_name", "bb_set_kernel_override",
+    "bb_init", "bb_matmul", "bb_matmul_scatter", "bb_peer_barrier", "bb_workspace_bytes", "bb_select_kernel", "bb_kernel_name", "bb_set_kernel_override",
     "bb_launch_count", "bb_last_error", "bb_version", "bb_compress_host", "bb_interleave_host",
     "bb_transform_weight_device", "bb_repack_gptq_qweight_device", "bb_repack_gptq_qzeros_device",
     "bb_retile_weight_device", "bb_debug_decode", "bb_debug_dequant",
@@ -64,6 +65,7 @@ def load() -> ctypes.CDLL:
     lib.bb_matmul.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, i32, vp, sz, vp]; lib.bb_matmul.restype = i32
     lib.bb_matmul_scatter.argtypes = [dp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), i32, i64, i64, i32, vp, sz, vp]
     lib.bb_matmul_scatter.restype = i32
+    lib.bb_peer_barrier.argtypes = [ctypes.POINTER(vp), i32, i32, vp]; lib.bb_peer_barrier.restype = i32
     lib.bb_workspace_bytes.argtypes = [dp, i32]; lib.bb_workspace_bytes.restype = sz
     lib.bb_select_kernel.argtypes = [dp, i32]; lib.bb_select_kernel.restype = i32
     lib.bb_kernel_name.argtypes = [i32]; lib.bb_kernel_name.restype = ctypes.c_char_p

@@ -109,6 +109,40 @@ static int select(const bb_matmul_desc& d, int m) {
   return BB_KERNEL_GENERIC;
 }
 
+// ---- cross-rank barrier of the column-parallel path -------------------------------------------------------------------
+// One tiny kernel instead of a library collective: every rank bumps its own sequence number, release-stores it into slot [rank] of
+// every peer's flag block (peer-mapped symmetric memory, NVLink) and acquire-spins until all of its own slots reached it.  The kernel
+// is launched with the programmatic-dependent-launch attribute and starts with griddepcontrol.wait: all memory operations of the
+// preceding matmul kernel(s) -- the peer stores of bb_matmul_scatter -- are complete and visible before the flag goes out, and
+// the next matmul kernel (a programmatic dependent of this one) fetches its first weights while this one spins.
+// Flag block (per rank, symmetric, zero-initialised once): uint32 slot[BB_MAX_PEERS]; uint32 pad[8]; uint32 seq (index 16).
+struct PeerBarrierArgs { uint32_t* flags[BB_MAX_PEERS]; int n, rank; };
+
+__global__ void peer_barrier_kernel(const PeerBarrierArgs a) {
+  __shared__ uint32_t seq_s;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  uint32_t* mine = a.flags[a.rank];
+  if (threadIdx.x == 0) {
+    const uint32_t seq = mine[16] + 1u;
+    mine[16] = seq;
+    seq_s = seq;
+  }
+  __syncthreads();
+  const uint32_t seq = seq_s;
+  const int p = threadIdx.x;
+  if (p < a.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[p] + a.rank), "r"(seq) : "memory");
+    const long long t0 = clock64();
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + p) : "memory");
+      if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s at 2 GHz: a peer died; fail the launch instead of hanging the GPU
+    } while (int(v - seq) < 0);
+  }
+}
+
 }  // namespace bb
 
 using namespace bb;
@@ -221,6 +255,26 @@ int bb_matmul_scatter(const bb_matmul_desc* desc, const void* A, const void* W, 
   if (n_peers < 1) { set_error("bb_matmul_scatter needs n_peers >= 1"); return 1; }
   return matmul_impl(desc, A, W, lut, scale, zeros, bias, nullptr, peer_C, n_peers, ldc, col_offset, m, workspace,
                      workspace_bytes, stream);
+}
+
+int bb_peer_barrier(void* const* peer_flags, int n_peers, int rank, void* stream) {
+  if (!peer_flags || n_peers < 1 || n_peers > BB_MAX_PEERS || rank < 0 || rank >= n_peers) {
+    set_error("bb_peer_barrier: need 1 <= n_peers <= %d flag blocks and 0 <= rank < n_peers", BB_MAX_PEERS);
+    return 1;
+  }
+  PeerBarrierArgs a;
+  for (int i = 0; i < BB_MAX_PEERS; ++i) a.flags[i] = i < n_peers ? reinterpret_cast<uint32_t*>(peer_flags[i]) : nullptr;
+  for (int i = 0; i < n_peers; ++i) if (!a.flags[i] || (reinterpret_cast<uintptr_t>(a.flags[i]) & 3)) { set_error("bb_peer_barrier: flag block %d is null or unaligned", i); return 1; }
+  a.n = n_peers; a.rank = rank;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  BB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, peer_barrier_kernel, a));
+  BB_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // extern "C"

@@ -23,6 +23,37 @@ import torch.nn as nn
 from .module import Linear
 
 
+class PeerBarrier:
+    """Device-side barrier across the ranks of a group, one small kernel per call (bb_peer_barrier): ordered after the peer stores
+    of the preceding bb_matmul_scatter launches on the same stream, CUDA-graph capturable, and -- being a programmatic dependent
+    launch -- overlapped with the next matmul kernel's weight prefetch.  Replaces the symmetric-memory library barrier on the
+    fused column-parallel path (measured at 2 GPUs: ~14 us per step for the library barrier, profiles/r2_multi_2gpu.txt)."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.flags = symm_mem.empty((_lib.BB_PEER_FLAG_BYTES // 4,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.handle = symm_mem.rendezvous(self.flags, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
+        torch.cuda.synchronize(device)
+        self.handle.barrier(channel=0)          # every rank's flag block is zeroed before anyone signals into it
+        torch.cuda.synchronize(device)
+        self.device = device
+
+    def __call__(self, stream=None):
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        rc = self._lib.bb_peer_barrier(self._arr, self.world, self.rank, st.cuda_stream)
+        if rc != 0:
+            from . import _lib
+            raise RuntimeError(f"bb_peer_barrier failed (code {rc}): {_lib.last_error()}")
+
+
 def shard_bounds(n: int, rank: int, world: int, multiple: int = 16):
     if n % world:
         raise ValueError(f"N={n} is not divisible by world size {world}")
@@ -73,6 +104,7 @@ class ColumnParallelLinear(nn.Module):
         self.clone_output = bool(clone_output)
         self._fused_decided = fused_gather is False
         self._symm = {}       # (rows capacity, dtype) -> [ring of (tensor, handle, peer pointer array), next index]
+        self._barrier = None  # PeerBarrier, created with the first symmetric buffer
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
@@ -137,7 +169,9 @@ class ColumnParallelLinear(nn.Module):
         # every rank's slice has landed in every buffer once all ranks passed this point.  Buffers alternate between calls:
         # a rank can only overwrite buffer b again after the NEXT call's barrier, which every peer reaches after its
         # (stream-ordered) reads of this call's result.
-        hdl.barrier(channel=0)
+        if self._barrier is None:
+            self._barrier = PeerBarrier(x2.device, self.group)
+        self._barrier()
         return buf[:m].clone() if self.clone_output else buf[:m]
 
     def _fused_supported_here(self, x2: torch.Tensor) -> bool:
@@ -207,4 +241,98 @@ class ColumnParallelLinear(nn.Module):
         return full.reshape(*lead, self.out_features)
 
 
-__all__ = ["ColumnParallelLinear", "shard_quantized_params", "shard_bounds"]
+def shard_quantized_params_k(qweight, scales, zeros, *, rank: int, world: int, K: int, bits: int, group_size: int,
+                             zeros_mode: str = "original"):
+    """Slice full-size BitBLAS-layout parameters along K (input features) for one rank of a row-parallel layer.  The shard
+    boundary must fall on a group boundary and on a 32-bit storage word (the LOP3 interleave permutes inside one word only, so a
+    word-aligned K range of an interleaved row is the interleaved row of that K range).  Row-major storage only: slab-tiled
+    weights are un-tiled by the caller first (RowParallelLinear.load_full_params does)."""
+    if K % world:
+        raise ValueError(f"K={K} is not divisible by world size {world}")
+    per = K // world
+    g = K if group_size in (-1, None) else group_size
+    if per % g:
+        raise ValueError(f"K/world = {per} must be a multiple of the group size {g}")
+    if (per * bits) % 32:
+        raise ValueError(f"K/world = {per} must cover whole 32-bit storage words at {bits} bits")
+    lo, hi = rank * per, (rank + 1) * per
+    out = {"qweight": qweight[:, lo * bits // 8:hi * bits // 8].contiguous()}
+    if scales is not None:
+        out["scales"] = scales[:, lo // g:hi // g].contiguous()
+    if zeros is not None:
+        out["zeros"] = (zeros[lo // g:hi // g] if zeros_mode == "quantized" else zeros[:, lo // g:hi // g]).contiguous()
+    return out
+
+
+class RowParallelLinear(nn.Module):
+    """y = sum_r x[:, K_r] @ dequant(W[:, K_r])^T (+ b): W sharded along K (input features) across the group -- the second half
+    of a tensor-parallel MLP / attention block (column-parallel up-projection, row-parallel down-projection: the activations arrive
+    already sharded, only the output is exchanged).  The reference has no distributed code; this is SURVEY.md 8(f)'s
+    "row-parallel" item.  Each rank runs the ordinary low-bit matmul on its K slice with fp32 output, the partial sums meet in ONE
+    all-reduce (NCCL: in-switch NVLS reduction on NVSwitch systems), bias is added once, the result is cast to out_dtype.
+    Unlike the column-parallel layer the exchange moves REDUCED data: it cannot be expressed as peer stores from the epilogue
+    without atomics, so it stays a collective (a reduce-scatter epilogue over multimem.red is the follow-up)."""
+
+    def __init__(self, in_features: int, out_features: int, *, process_group=None, input_is_parallel: bool = True,
+                 bias: bool = False, out_dtype: str = "float16", **linear_kwargs):
+        super().__init__()
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        if in_features % self.world:
+            raise ValueError(f"in_features={in_features} is not divisible by world size {self.world}")
+        self.in_features, self.out_features = in_features, out_features
+        self.k_per = in_features // self.world
+        self.k_lo, self.k_hi = self.rank * self.k_per, (self.rank + 1) * self.k_per
+        self.input_is_parallel = input_is_parallel
+        self.final_dtype = getattr(torch, out_dtype)
+        gs = linear_kwargs.get("group_size", -1)
+        if gs in (-1, None):
+            linear_kwargs["group_size"] = in_features      # "whole row" groups stay whole-row groups of the FULL K: one scale per
+            if self.world > 1:                            # row cannot be split -- each shard then uses the same scale column
+                linear_kwargs["group_size"] = self.k_per
+        # partial sums leave the kernel in fp32 (the all-reduce must not round per rank); bias is added after the reduction
+        self.local = Linear(self.k_per, out_features, bias=False, out_dtype="float32" if self.world > 1 else out_dtype, **linear_kwargs)
+        self._whole_row_groups = gs in (-1, None)
+        self.register_buffer("bias", torch.zeros((out_features,), dtype=self.final_dtype) if bias else None)
+
+    def load_full_params(self, qweight, scales=None, zeros=None, bias=None):
+        """full-size parameters in the operator's own storage (as produced by Matmul.transform_weight of the FULL layer, row-major
+        or slab-tiled per this layer's propagate_b) -> this rank's K shard."""
+        op = self.local.bitblas_matmul
+        if op.weight_tiled:
+            qweight = op.tile_weight(qweight, inverse=True)
+        g = self.in_features if self._whole_row_groups else op.config.group_size
+        if self._whole_row_groups and scales is not None and self.world > 1:
+            # one group spanning the full K: every shard multiplies by the same per-row scale (and zero point)
+            sh = {"qweight": qweight[:, self.k_lo * op.bit // 8:self.k_hi * op.bit // 8].contiguous(), "scales": scales.contiguous()}
+            if zeros is not None:
+                sh["zeros"] = zeros.contiguous()
+        else:
+            sh = shard_quantized_params_k(qweight, scales, zeros, rank=self.rank, world=self.world, K=self.in_features, bits=op.bit,
+                                          group_size=g, zeros_mode=op.config.zeros_mode)
+        dev = self.local.qweight.device
+        w = sh["qweight"].to(dev)
+        self.local.qweight = op.tile_weight(w) if op.weight_tiled else w
+        if "scales" in sh:
+            self.local.scales = sh["scales"].to(dev)
+        if "zeros" in sh:
+            self.local.zeros = sh["zeros"].to(dev)
+        if bias is not None and self.bias is not None:
+            self.bias = bias.to(dev).to(self.final_dtype)
+        self.local.q_params = None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        xs = x if self.input_is_parallel else x[..., self.k_lo:self.k_hi]
+        if xs.shape[-1] != self.k_per:
+            raise ValueError(f"expected the K shard of width {self.k_per}, got {xs.shape[-1]}")
+        part = self.local(xs.contiguous())
+        if self.world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        out = part if part.dtype == self.final_dtype else part.to(self.final_dtype)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
+__all__ = ["PeerBarrier", "ColumnParallelLinear", "RowParallelLinear", "shard_quantized_params", "shard_quantized_params_k", "shard_bounds"]

@@ -136,6 +136,15 @@ int bb_matmul_scatter(const bb_matmul_desc* desc, const void* A, const void* W, 
                       const void* zeros, const void* bias, void* const* peer_C, int n_peers, int64_t ldc,
                       int64_t col_offset, int m, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Cross-rank barrier for the column-parallel path (no reference counterpart): rank `rank` of `n_peers` signals every peer and
+ * waits for all of them, on `stream`, as ONE small kernel -- ordered after the preceding kernels' peer stores (it is launched as a
+ * programmatic dependent and waits for them), so after it every rank may read what bb_matmul_scatter calls issued before it wrote.
+ * peer_flags[i] = device pointer to rank i's flag block in peer-mapped (symmetric) memory, BB_PEER_FLAG_BYTES each, zeroed
+ * once before first use; every rank must call it the same number of times.  CUDA-graph capturable (sequence numbers live in the
+ * flag block, not in the launch parameters).  A peer that never arrives traps the kernel after ~10 s instead of hanging. */
+#define BB_PEER_FLAG_BYTES 128
+int bb_peer_barrier(void* const* peer_flags, int n_peers, int rank, void* stream);
+
 /* scratch (fp32 split-K partials; stream-K slots + flags) the chosen kernel needs for this (desc, m); 0 for most configs.
  * The buffer must be ZERO-INITIALISED once by the caller before its first use (cudaMemset / torch.zeros): the stream-K
  * kernels exchange partial sums through tagged slots and leave every slot zero-tagged again when they finish, so the same

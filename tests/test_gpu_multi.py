@@ -46,6 +46,25 @@ def _worker(rank, world, port, ret):
             torch.cuda.synchronize()
             assert torch.equal(out3.cpu(), out.cpu())
             ret[f"fused{rank}_{M}"] = fused_ok
+        # ---- row-parallel (K-sharded) layer: fp32 partial sums from the ordinary kernels, one NCCL all-reduce ----
+        import bitblas_b200 as bitblas
+        from bitblas_b200.parallel import RowParallelLinear
+        for M, tiled in ((1, False), (1, True), (48, False), (300, True)):
+            N, K, g = 256, 4096, 128
+            case = H.make_case(M, N, K, W_dtype="uint4", group_size=g, with_scaling=True, with_zeros=True, zeros_mode="quantized",
+                               with_bias=True, seed=9)
+            layer = RowParallelLinear(K, N, bias=True, input_is_parallel=False, A_dtype="float16", W_dtype="uint4", group_size=g,
+                                      with_scaling=True, with_zeros=True, zeros_mode="quantized", enable_tuning=False,
+                                      propagate_b=tiled).cuda()
+            full_op = bitblas.Matmul(bitblas.MatmulConfig(M=M, N=N, K=K, A_dtype="float16", W_dtype="uint4", group_size=g, with_scaling=True,
+                                                          with_zeros=True, zeros_mode="quantized", propagate_b=tiled), enable_tuning=False)
+            stored = full_op.transform_weight(case["fields"].to(torch.int8))
+            layer.load_full_params(stored, case["scale"], case["zeros"], case["bias"])
+            assert layer.local.bitblas_matmul.weight_tiled == tiled
+            out = layer(case["A"].cuda())
+            torch.cuda.synchronize()
+            H.assert_fp_close(out.cpu(), H.oracle_output(case), f"row-parallel M={M} tiled={tiled} rank={rank}")
+            ret[f"rowk{rank}_{M}_{int(tiled)}"] = layer.local.bitblas_matmul.kernel_for(M)
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -62,3 +81,4 @@ def test_column_parallel_nccl():
     d = dict(ret)
     assert d[0] == "ok" and d[1] == "ok", d
     print("fused gather used:", {k: v for k, v in d.items() if str(k).startswith("fused")})
+    print("row-parallel kernels:", {k: v for k, v in d.items() if str(k).startswith("rowk")})
