@@ -66,7 +66,8 @@ def profiled_traffic():
 def gemv_bytes(N, K, M=1, bits=4, g=GROUP, zeros="quantized", a_bytes=2, out_bytes=2):
     """algorithmic bytes, SURVEY.md §8(d): W + scale + zeros + A + C."""
     b = N * K * bits // 8 + N * (K // g) * 2
-    b += (K // g) * N * bits // 8 if zeros == "quantized" else N * (K // g) * 2
+    if zeros != "none":
+        b += (K // g) * N * bits // 8 if zeros == "quantized" else N * (K // g) * 2
     return b + M * K * a_bytes + M * N * out_bytes
 
 
@@ -370,7 +371,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--only", default="", help="comma list of sections to run: gemm,llama,w2a8,e2e (default all; the GEMV step always runs)")
+    ap.add_argument("--only", default="", help="comma list of sections to run: gemm,llama,w2a8,formats,e2e (default all; the GEMV step always runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -645,6 +646,30 @@ def main():
             w2.append(row)
         result["w2a8"] = w2
         result["int8_peak_tops_measured"] = round(i8peak, 1) if i8peak else None
+
+    # ---------------- table formats (NF4) on the fast kernels: decode GEMV and tcgen05 GEMM at the target shape ----------------
+    if want("formats") and world == 1:
+        N, K = 12288, 12288
+        cfgn = bitblas.MatmulConfig(M=[1, 4096], N=N, K=K, A_dtype="float16", W_dtype="nf4", accum_dtype="float16", out_dtype="float16",
+                                    group_size=GROUP, with_scaling=True, with_zeros=False)
+        opn = bitblas.Matmul(cfgn, enable_tuning=False)
+        gn = torch.Generator(device=dev).manual_seed(5)
+        prmn = dict(W=torch.randint(-128, 128, opn.retrieve_weight_shape(), generator=gn, dtype=torch.int8, device=dev),
+                    scale=(torch.rand((N, K // GROUP), generator=gn, device=dev) * 0.02 + 0.002).half(), zeros=None)
+        An = (torch.rand((1, K), device=dev) - 0.5).half()
+        outn = torch.empty((1, N), dtype=torch.float16, device=dev)
+        tn, _, _ = rotating_kernel_time(opn, prmn, An, outn)
+        bn = gemv_bytes(N, K, zeros="none")
+        rowsn = [{"W_dtype": "nf4", "M": 1, "us": round(tn * 1e3, 2), "GBps": round(bn / (tn * 1e-3) / 1e9, 1),
+                  "frac_hbm": round(bn / (tn * 1e-3) / 1e9 / pk["hbm"], 3), "kernel": opn.kernel_for(1)}]
+        A4 = (torch.rand((4096, K), device=dev) - 0.5).half()
+        out4 = torch.empty((4096, N), dtype=torch.float16, device=dev)
+        ms4 = timed(lambda: opn.forward(A4, prmn["W"], scale=prmn["scale"], output=out4), 10, 3)
+        tf4 = 2.0 * 4096 * N * K / (ms4 * 1e-3) / 1e12
+        rowsn.append({"W_dtype": "nf4", "M": 4096, "us": round(ms4 * 1e3, 1), "TFLOPS": round(tf4, 1), "frac_tensor": round(tf4 / pk["tf"], 3),
+                      "kernel": opn.kernel_for(4096)})
+        result["table_formats"] = rowsn
+        del opn, prmn, A4, out4
 
     # ---------------- e2e: public API, host activations in, host results out, one sync per step ----------------
     e2e = None

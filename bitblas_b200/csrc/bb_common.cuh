@@ -246,6 +246,55 @@ __device__ __forceinline__ uint32_t dq_finish(uint32_t x, uint32_t mz, const DqC
   return t;
 }
 
+// ---- 16-entry table formats (NF4: caller's LUT, matmul_dequantize_impl.py:424-430; "fp4": sign + 3-bit exponent,
+// quantization.py:141-156) decoded in registers with byte permutes ------------------------------------------------------------
+// The table of 16 x 16-bit A_dtype values is kept as two byte planes of 16 bytes (4 registers each).  One PRMT looks up four
+// 3-bit indices in 8 bytes; index bit 3 picks between the lower / upper half of the table with a second PRMT whose selector
+// is built from those bits: 21 ALU operations per packed word (8 weights), no shared-memory or constant-bank traffic.
+struct Lut4 { uint32_t lo[4], hi[4]; };
+
+__host__ __device__ constexpr uint16_t fp4_table_bits(int u, bool bf16) {
+  const int s = u >> 3, e = u & 7;
+  if (e == 0) return 0;                                                    // exponent field 0 decodes to 0 (quantization.py:150-156)
+  return bf16 ? uint16_t((s << 15) | ((120 + e) << 7))                     // 2^(e-7) in bfloat16
+              : uint16_t(((e | 8) | (s << 5)) << 10);                      // the reference's fp16 bit pattern
+}
+__device__ __forceinline__ void lut4_from_pairs(Lut4& t, const uint32_t (&r)[8]) {   // r[j] = (entry 2j, entry 2j+1)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    t.lo[k] = __byte_perm(r[2 * k], r[2 * k + 1], 0x6420);
+    t.hi[k] = __byte_perm(r[2 * k], r[2 * k + 1], 0x7531);
+  }
+}
+// fmt: BB_W_NF -> 16 entries from `lut` (A_dtype, any 2-byte alignment); BB_W_FP4 -> the fixed table
+__device__ __forceinline__ void lut4_init(Lut4& t, int fmt, bool bf16, const void* lut) {
+  uint32_t r[8];
+  if (fmt == BB_W_NF) {
+    const uint16_t* l = reinterpret_cast<const uint16_t*>(lut);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = uint32_t(__ldg(l + 2 * j)) | (uint32_t(__ldg(l + 2 * j + 1)) << 16);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      r[j] = bf16 ? (uint32_t(fp4_table_bits(2 * j, true)) | (uint32_t(fp4_table_bits(2 * j + 1, true)) << 16))
+                  : (uint32_t(fp4_table_bits(2 * j, false)) | (uint32_t(fp4_table_bits(2 * j + 1, false)) << 16));
+  }
+  lut4_from_pairs(t, r);
+}
+// compressed storage (element j in nibble j): out[i] = (T[e(2i)], T[e(2i+1)])  i = 0..3
+__device__ __forceinline__ void lut4_decode8(uint32_t w, const Lut4& t, uint32_t (&out)[4]) {
+  const uint32_t s7 = w & 0x77777777u;                              // 3-bit indices (a selector's bit 3 would sign-replicate)
+  const uint32_t pk = ((w >> 1) & 0x44444444u) | 0x32103210u;       // byte k of (lower-half result | upper-half result)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t s = h ? (s7 >> 16) : s7, p = h ? (pk >> 16) : pk;
+    const uint32_t l4 = __byte_perm(__byte_perm(t.lo[0], t.lo[1], s), __byte_perm(t.lo[2], t.lo[3], s), p);
+    const uint32_t h4 = __byte_perm(__byte_perm(t.hi[0], t.hi[1], s), __byte_perm(t.hi[2], t.hi[3], s), p);
+    out[2 * h] = __byte_perm(l4, h4, 0x5140);
+    out[2 * h + 1] = __byte_perm(l4, h4, 0x7362);
+  }
+}
+
 // ---- in-register decode of packed low-bit words -----------------------------------------------
 // 4-bit, 16-bit target.  Returns raw "magic + u" pairs (bias removed by the caller with one sub/fma).
 //   interleaved layout (quantization/utils.py:73-110): out[i] = (u[2i], u[2i+1])       i = 0..3

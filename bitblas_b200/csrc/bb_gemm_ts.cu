@@ -179,6 +179,8 @@ struct TsParams {
   int splits;        // split-K factor (>1: fp32 / int32 partials go to `ws`, reduced by splitk_reduce_kernel)
   int kb_per_split;  // k-blocks per split
   void* ws;          // [splits][M][N] partials
+  const void* lut;   // NF4 table (16 x A_dtype), null otherwise
+  int w_fmt;         // bb_wfmt (the table formats run the FMT = 1 instances)
   int w_tiled;       // BB_TILE_SLAB weight storage: tmW is the 4-D map {512 B, 32 rows, segments per row, row blocks}
   int staged_epi;    // 16-bit outputs: transpose the accumulator tile through shared memory, 16-byte row-major stores (see epilogue)
 };
@@ -291,6 +293,44 @@ __device__ __forceinline__ void dequant_half_row(uint32_t src, uint32_t (&out)[1
   }
 }
 
+// table formats (NF4 / fp4), compressed storage: 16 packed bytes -> 32 values in natural k order; MODE 0 none, 1 scale
+template <typename T, int MODE>
+__device__ __forceinline__ void dequant_half_row_lut(uint32_t src, uint32_t (&out)[16], const Lut4& t, uint32_t s2) {
+  const uint4 pk = lds128(src);
+  const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t h[4];
+    lut4_decode8(w[i], t, h);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[4 * i + j] = MODE == 1 ? mul2<T>(h[j], s2) : h[j];
+  }
+}
+
+// 8-bit float weights (e4m3_float8 / e5m2_float8 with 16-bit activations): 32 bytes -> 32 values in natural k order.
+// e5m2 is the top byte of an fp16 (quantization.py:179-182); e4m3 follows the reference's bit trick (quantization.py:169-176:
+// sign | ((v & 63) << 7 | e4 << 8 | e4 << 7) ^ 0x2000 with e4 = v & 0x40), evaluated on two bytes at a time.  bf16 activations:
+// the fp16 pair is widened exactly (every fp8 value is representable in bf16).
+template <typename T, int MODE>
+__device__ __forceinline__ void dequant_half_row_fp8(uint32_t src, uint32_t (&out)[16], bool e5m2, uint32_t s2) {
+  const uint4 p0 = lds128(src), p1 = lds128(src + 16);
+  const uint32_t w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t x = __byte_perm(w[i], 0u, j ? 0x3424 : 0x1404);   // (byte 2j) << 8 | (byte 2j+1) << 24
+      uint32_t h = x;
+      if (!e5m2) h = ((x & 0xC000C000u) | ((x >> 1) & 0x3F803F80u)) ^ 0x20002000u;
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        const float2 f = __half22float2(u32_as_h2(h));
+        h = b2_as_u32(__floats2bfloat162_rn(f.x, f.y));
+      }
+      out[2 * i + j] = MODE == 1 ? mul2<T>(h, s2) : h;
+    }
+  }
+}
+
 template <int BITS, bool IL>
 __device__ __forceinline__ void dequant_half_row_i8(uint32_t src, uint32_t (&out)[16], uint32_t zp4) {
   if constexpr (BITS == 2) {
@@ -333,7 +373,9 @@ __device__ __forceinline__ void dequant_half_row_i8(uint32_t src, uint32_t (&out
   }
 }
 
-template <typename T, int BITS, int BM, bool IL>
+// FMT: 0 = integer formats (LOP3 magic-number decode), 1 = 16-entry table formats (NF4 / fp4; BITS = 4, compressed storage),
+//      2 = 8-bit float weights (e4m3 / e5m2; BITS = 8)
+template <typename T, int BITS, int BM, bool IL, int FMT = 0>
 __global__ void __launch_bounds__(TS_THREADS, BM <= 128 ? 2 : 1)
 gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TsParams p) {
   using SM = TsSmem<T, BITS, BM>;
@@ -462,6 +504,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t src0 = smem_u32(sW) + row * PRB + half * (PRB / 2);
     const uint32_t tdst0 = lane_addr + ACOL0 + half * 16;
 
+    Lut4 lut4;
+    if constexpr (FMT == 1) lut4_init(lut4, p.w_fmt, std::is_same<TF, __nv_bfloat16>::value, p.lut);
     auto dq_loop = [&](auto mode_tag) {
       constexpr int MODE = decltype(mode_tag)::value;
       DqConst c;
@@ -523,6 +567,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&full[st], full_par);
         uint32_t regs[16];
         if constexpr (INT8) dequant_half_row_i8<BITS, IL>(src0 + st * SM::kWBytes, regs, uint32_t(p.zp_const) * 0x01010101u);
+        else if constexpr (FMT == 1) dequant_half_row_lut<TF, MODE>(src0 + st * SM::kWBytes, regs, lut4, c.s2);
+        else if constexpr (FMT == 2) dequant_half_row_fp8<TF, MODE>(src0 + st * SM::kWBytes, regs, p.w_fmt == BB_W_FP8_E5M2, c.s2);
         else dequant_half_row<TF, BITS, MODE, IL>(src0 + st * SM::kWBytes, regs, c);
         // publish the PREVIOUS k-block's TMEM slot only now: its tcgen05.st had the whole decode above to land
         if (prev_slot >= 0) {
@@ -539,6 +585,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_st_x16(tdst0 + slot * 32, regs);
         if constexpr (WHOLE_ROW) {
           if constexpr (INT8) dequant_half_row_i8<BITS, IL>(src0 + st * SM::kWBytes + PRB / 2, regs, uint32_t(p.zp_const) * 0x01010101u);
+          else if constexpr (FMT == 1) dequant_half_row_lut<TF, MODE>(src0 + st * SM::kWBytes + PRB / 2, regs, lut4, c.s2);
+          else if constexpr (FMT == 2) dequant_half_row_fp8<TF, MODE>(src0 + st * SM::kWBytes + PRB / 2, regs, p.w_fmt == BB_W_FP8_E5M2, c.s2);
           else dequant_half_row<TF, BITS, MODE, IL>(src0 + st * SM::kWBytes + PRB / 2, regs, c);
           tmem_st_x16(tdst0 + slot * 32 + 16, regs);
         }
@@ -556,6 +604,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     if constexpr (INT8) {
       dq_loop(std::integral_constant<int, 0>{});
+    } else if constexpr (FMT != 0) {   // table / fp8 formats: no zero points on the fast path (gemm_ts_supported)
+      if (p.mode == 0) dq_loop(std::integral_constant<int, 0>{}); else dq_loop(std::integral_constant<int, 1>{});
     } else {
       switch (p.mode) {
         case 0: dq_loop(std::integral_constant<int, 0>{}); break;
@@ -830,11 +880,11 @@ int make_map_w_tiled(CUtensorMap* map, const void* base, uint64_t row_bytes, uin
   return 0;
 }
 
-template <typename T, int BITS, int BM, bool IL>
+template <typename T, int BITS, int BM, bool IL, int FMT = 0>
 int launch_ts_inst(const MatmulArgs& a, const TsParams& p0) {
   using SM = TsSmem<T, BITS, BM>;
   using EI = ElemInfo<T>;
-  auto kernel = gemm_ts_kernel<T, BITS, BM, IL>;
+  auto kernel = gemm_ts_kernel<T, BITS, BM, IL, FMT>;
   static bool attr_set[BB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
   const int dev = current_device();
   if (!attr_set[dev]) {
@@ -903,6 +953,20 @@ int launch_ts_bm2(const MatmulArgs& a, const TsParams& p) {
   if (a.m <= 128) return launch_ts_inst<T, BITS, 128, IL>(a, p);
   return launch_ts_inst<T, BITS, 256, IL>(a, p);
 }
+template <typename T>
+int launch_ts_lut(const MatmulArgs& a, const TsParams& p) {
+  if (a.m <= 32) return launch_ts_inst<T, 4, 32, false, 1>(a, p);
+  if (a.m <= 64) return launch_ts_inst<T, 4, 64, false, 1>(a, p);
+  if (a.m <= 128) return launch_ts_inst<T, 4, 128, false, 1>(a, p);
+  return launch_ts_inst<T, 4, 256, false, 1>(a, p);
+}
+template <typename T>
+int launch_ts_fp8(const MatmulArgs& a, const TsParams& p) {
+  if (a.m <= 32) return launch_ts_inst<T, 8, 32, false, 2>(a, p);
+  if (a.m <= 64) return launch_ts_inst<T, 8, 64, false, 2>(a, p);
+  if (a.m <= 128) return launch_ts_inst<T, 8, 128, false, 2>(a, p);
+  return launch_ts_inst<T, 8, 256, false, 2>(a, p);
+}
 template <typename T, int BITS>
 int launch_ts_bm(const MatmulArgs& a, const TsParams& p) {
   return a.d.w_layout == BB_LAYOUT_COMPRESSED ? launch_ts_bm2<T, BITS, false>(a, p) : launch_ts_bm2<T, BITS, true>(a, p);
@@ -912,8 +976,15 @@ int launch_ts_bm(const MatmulArgs& a, const TsParams& p) {
 
 bool gemm_ts_supported(const bb_matmul_desc& d, int m) {
   if (m < 1) return false;
-  if (d.w_fmt != BB_W_UINT && d.w_fmt != BB_W_INT) return false;
-  if (d.w_bits != 4 && d.w_bits != 2) return false;
+  const bool table_fmt = d.w_fmt == BB_W_NF || d.w_fmt == BB_W_FP4;
+  if (table_fmt) {   // 16-entry table formats: 4-bit compressed storage, scale only (a zero point has no fast path)
+    if (d.w_bits != 4 || d.w_layout != BB_LAYOUT_COMPRESSED || d.with_zeros || d.a_dtype == BB_I8) return false;
+  } else if (d.w_fmt == BB_W_FP8_E4M3 || d.w_fmt == BB_W_FP8_E5M2) {   // 8-bit float weights x 16-bit activations, scale only
+    if (d.w_bits != 8 || d.w_layout != BB_LAYOUT_COMPRESSED || d.with_zeros || d.a_dtype == BB_I8) return false;
+  } else if (d.w_fmt != BB_W_UINT && d.w_fmt != BB_W_INT) {
+    return false;
+  }
+  if (d.w_bits != 4 && d.w_bits != 2 && !(d.w_bits == 8 && (d.w_fmt == BB_W_FP8_E4M3 || d.w_fmt == BB_W_FP8_E5M2))) return false;
   if (d.N % TS_ROWS) return false;
   const int g = d.group_size <= 0 ? d.K : d.group_size;
   if (d.a_dtype == BB_I8) {
@@ -957,6 +1028,10 @@ int launch_gemm_ts(const MatmulArgs& a) {
   p.mode = !d.with_scaling ? 0 : (!d.with_zeros ? 1 : 2 + d.zeros_mode);
   p.zp_const = d.w_fmt == BB_W_INT ? (1 << (d.w_bits - 1)) : 0;
   p.out_dtype = d.out_dtype; p.a_dtype = d.a_dtype; p.m_tiles = 1;
+  p.lut = d.w_fmt == BB_W_NF ? a.lut : nullptr;
+  p.w_fmt = d.w_fmt;
+  if (d.w_fmt == BB_W_NF || d.w_fmt == BB_W_FP4) return d.a_dtype == BB_F16 ? launch_ts_lut<__half>(a, p) : launch_ts_lut<__nv_bfloat16>(a, p);
+  if (d.w_fmt == BB_W_FP8_E4M3 || d.w_fmt == BB_W_FP8_E5M2) return d.a_dtype == BB_F16 ? launch_ts_fp8<__half>(a, p) : launch_ts_fp8<__nv_bfloat16>(a, p);
   if (d.a_dtype == BB_I8) return d.w_bits == 4 ? launch_ts_bm<int8_t, 4>(a, p) : launch_ts_bm<int8_t, 2>(a, p);
   if (d.a_dtype == BB_F16) return d.w_bits == 4 ? launch_ts_bm<__half, 4>(a, p) : launch_ts_bm<__half, 2>(a, p);
   return d.w_bits == 4 ? launch_ts_bm<__nv_bfloat16, 4>(a, p) : launch_ts_bm<__nv_bfloat16, 2>(a, p);

@@ -89,6 +89,8 @@ struct SlabParams {
   unsigned int nonce;
   int dbg;          // tuning diagnostics (BB_GS_DBG): 1 = consumers skip the arithmetic, 4 = no sums, 16 = no parameter conversion
                     // (results are wrong with any of them set)
+  const void* lut;   // NF4 table (16 x A_dtype) for the FMT = 1 instances, else null
+  int w_fmt;         // bb_wfmt
   const uint8_t* Wt; // BB_TILE_SLAB storage (else null): unit (rb, ku) is the contiguous 16 KB block number rb * UPR + ku
   int fast_params;  // group size 128, 8-aligned group count, N % 32 == 0, aligned pointers: 16-byte async copies of the parameters
 };
@@ -212,11 +214,13 @@ __device__ __forceinline__ int gs_range_begin(int ri, int T, int R) { return int
 // time, the tuning / test variant): with a constant depth every stage address is base + immediate -- the run-time variant spends
 // ~40 integer instructions per unit and warp re-deriving the region bases (profiles/r2_gemv_slab_ncu_full.txt, SASS page)
 // NF = finisher warps (S % NF == 0; finisher f serves the units i = f (mod NF) of the range)
-template <typename T, bool IL, int NG, int MINB, int SC, int NF>
+// FMT: 0 = uint4 / int4 (LOP3 magic decode, magic and zero point removed through the activation sums), 1 = 16-entry table formats
+// (NF4 / fp4, compressed storage: PRMT table decode to exact A_dtype values, scale only -- the sums are not needed)
+template <typename T, bool IL, int NG, int MINB, int SC, int NF, int FMT = 0>
 __global__ void __launch_bounds__(gs_threads(NG, NF), MINB)
 gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   constexpr bool F16 = std::is_same<T, __half>::value;
-  constexpr bool HI = F16;   // odd nibbles decoded in place (mantissa bits 4..7 under exponent 2^6: exactly 64 + u)
+  constexpr bool HI = F16 && FMT == 0;   // odd nibbles decoded in place (mantissa bits 4..7 under exponent 2^6: exactly 64 + u)
   constexpr uint32_t MAGIC = TypeTraits<T>::kMagic;
   constexpr uint32_t MAGIC_HI = 0x54005400u;
   constexpr int NCW = GS_GW * NG;            // consumer warps
@@ -343,7 +347,8 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
     {
       const uint32_t one2 = F16 ? 0x3c003c00u : 0x3f803f80u;
       uint32_t pat;
-      if (!HI) pat = MAGIC;                                   // (magic, magic)
+      if (FMT == 1) pat = 0u;                                  // table formats decode to the exact value: nothing to remove
+      else if (!HI) pat = MAGIC;                               // (magic, magic)
       else if (IL) pat = (t4 & 1) ? MAGIC_HI : MAGIC;          // elements {2,3,6,7} of a word sit in odd nibbles
       else pat = 0x54006400u;                                  // (even element: 1024, odd element: 64)
       if (g8 == 0) { sfrag[0] = one2; sfrag[2] = one2; }
@@ -467,6 +472,8 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
   const uint32_t redg = Rb + uint32_t(grp) * GS_RED_GROUP_BYTES;
   const int nsl_last = (Kb - (UPR - 1) * GS_ROW_BYTES) / GS_SLICE_BYTES;   // valid K-slices of a row block's last unit
 
+  Lut4 lut4;
+  if constexpr (FMT == 1) lut4_init(lut4, p.w_fmt, !F16, p.lut);
   uint32_t Rv[4][4];   // activations of the lane's chunk (lanes 0..7); other lanes feed unused MMA columns
 #pragma unroll
   for (int x = 0; x < 4; ++x)
@@ -516,7 +523,10 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
 #pragma unroll
         for (int wi = 0; wi < 4; ++wi) {
           uint32_t ha[4], hb[4];
-          if constexpr (HI) {
+          if constexpr (FMT == 1) {
+            lut4_decode8(wa[wi], lut4, ha);      // natural pairs (e0,e1) .. (e6,e7): the activation registers pair up as stored
+            lut4_decode8(wb[wi], lut4, hb);
+          } else if constexpr (HI) {
             const uint32_t xa = wa[wi], ya = wa[wi] >> 8, xb = wb[wi], yb = wb[wi] >> 8;
             ha[0] = lop3_and_or(xa, 0x000f000fu, MAGIC); ha[1] = lop3_and_or(xa, 0x00f000f0u, MAGIC_HI);
             ha[2] = lop3_and_or(ya, 0x000f000fu, MAGIC); ha[3] = lop3_and_or(ya, 0x00f000f0u, MAGIC_HI);
@@ -530,7 +540,7 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
           for (int jj = 0; jj < 2; ++jj) {
             const uint32_t af[4] = {ha[2 * jj], hb[2 * jj], ha[2 * jj + 1], hb[2 * jj + 1]};
             uint32_t b0, b1;
-            if constexpr (IL) {
+            if constexpr (IL || FMT == 1) {
               b0 = Rv[wi][2 * jj]; b1 = Rv[wi][2 * jj + 1];
             } else {
               b0 = __byte_perm(Rv[wi][jj], Rv[wi][jj + 2], 0x5410);
@@ -721,7 +731,12 @@ size_t gemv_slab_workspace_bytes() { return size_t(4) * size_t(device_sm_count()
 bool gemv_slab_supported(const bb_matmul_desc& d, int m) {
   if (m != 1) return false;
   if (d.a_dtype != BB_F16 && d.a_dtype != BB_BF16) return false;
-  if (d.w_fmt != BB_W_UINT && d.w_fmt != BB_W_INT) return false;
+  const bool table_fmt = d.w_fmt == BB_W_NF || d.w_fmt == BB_W_FP4;
+  if (table_fmt) {   // NF4 / fp4: compressed storage, scale only
+    if (d.w_layout != BB_LAYOUT_COMPRESSED || d.with_zeros) return false;
+  } else if (d.w_fmt != BB_W_UINT && d.w_fmt != BB_W_INT) {
+    return false;
+  }
   if (d.w_bits != 4) return false;
   if (d.w_layout == BB_LAYOUT_INTERLEAVED_8) return false;
   if (d.N % 16 || d.K % 256) return false;
@@ -748,7 +763,8 @@ int launch_gemv_slab(const MatmulArgs& a) {
   }
   const int dev = current_device();
   // consumer groups per CTA x CTAs per SM: (4, 1) shares one deep ring between four groups, (2, 2) runs two CTAs per SM
-  const int ng = env_int("BB_GS_NG", 2) == 4 ? 4 : 2;
+  const bool table_fmt = d.w_fmt == BB_W_NF || d.w_fmt == BB_W_FP4;
+  const int ng = (!table_fmt && env_int("BB_GS_NG", 2) == 4) ? 4 : 2;
   const int nf = env_int("BB_GS_NF", 1) == 2 ? 2 : 1;   // finisher warps of the (2 groups, 4 stages) configuration
   SlabParams p;
   p.A = a.A; p.scale = d.with_scaling ? a.scale : nullptr; p.zeros = d.with_zeros ? a.zeros : nullptr;
@@ -763,7 +779,9 @@ int launch_gemv_slab(const MatmulArgs& a) {
   p.T = ((p.NRB + ng - 1) / ng) * p.UPR * ng;
   // the ring depth must be a multiple of the group count: slot s then always belongs to group s % NG, which therefore sees every
   // phase of the slot's barriers (a group that skipped a phase would mistake the parity of a later one for its own)
-  int stages = env_int("BB_GS_STAGES", ng == 4 ? 8 : 4);
+  p.lut = d.w_fmt == BB_W_NF ? a.lut : nullptr;
+  p.w_fmt = d.w_fmt;
+  int stages = table_fmt ? 4 : env_int("BB_GS_STAGES", ng == 4 ? 8 : 4);
   stages = std::max(ng, std::min(GS_MAX_STAGES, stages) / ng * ng);
   p.stages = stages;
   p.dbg = env_int("BB_GS_DBG", 0);
@@ -787,9 +805,9 @@ int launch_gemv_slab(const MatmulArgs& a) {
   const int sms = device_sm_count();
   static const bool pdl = [] { const char* e = getenv("BB_PDL"); return e ? atoi(e) != 0 : true; }();
 
-#define BB_GS_GO(TT, ILV, NGV, MINBV, SCV, NFV, VAR)                                                   \
+#define BB_GS_GO(TT, ILV, NGV, MINBV, SCV, NFV, FMTV, VAR)                                                 \
   {                                                                                                    \
-    auto k = gemv_slab_kernel<TT, ILV, NGV, MINBV, SCV, NFV>;                                          \
+    auto k = gemv_slab_kernel<TT, ILV, NGV, MINBV, SCV, NFV, FMTV>;                                    \
     int occ = gs_occupancy(k, VAR, gs_threads(NGV, NFV), smem, dev);                                   \
     if (occ < 0) { set_error("gemv_slab: kernel does not fit on this device (stages=%d)", stages); return 4; } \
     occ = std::min(occ, MINBV);                                                                        \
@@ -806,11 +824,13 @@ int launch_gemv_slab(const MatmulArgs& a) {
   // the shipped configuration (2 groups, 4 stages) has the ring depth compiled in; every other knob setting runs the run-time-depth
   // variants (tuning sweeps, tests of the ring logic)
 #define BB_GS_NG(TT, ILV, VB)                                                  \
-  if (ng == 4) BB_GS_GO(TT, ILV, 4, 1, 0, 2, VB + 0)                           \
-  else if (stages == 4 && nf == 2) BB_GS_GO(TT, ILV, 2, 2, 4, 2, VB + 1)       \
-  else if (stages == 4) BB_GS_GO(TT, ILV, 2, 2, 4, 1, VB + 2)                  \
-  else BB_GS_GO(TT, ILV, 2, 2, 0, 1, VB + 3)
-  if (f16) { if (il) { BB_GS_NG(__half, true, 0) } else { BB_GS_NG(__half, false, 4) } }
+  if (ng == 4) BB_GS_GO(TT, ILV, 4, 1, 0, 2, 0, VB + 0)                           \
+  else if (stages == 4 && nf == 2) BB_GS_GO(TT, ILV, 2, 2, 4, 2, 0, VB + 1)       \
+  else if (stages == 4) BB_GS_GO(TT, ILV, 2, 2, 4, 1, 0, VB + 2)                  \
+  else BB_GS_GO(TT, ILV, 2, 2, 0, 1, 0, VB + 3)
+  if (table_fmt) {   // one instance per activation type: 2 groups x 2 CTAs/SM, 4 stages, 1 finisher
+    if (f16) BB_GS_GO(__half, false, 2, 2, 4, 1, 1, 16) else BB_GS_GO(__nv_bfloat16, false, 2, 2, 4, 1, 1, 17)
+  } else if (f16) { if (il) { BB_GS_NG(__half, true, 0) } else { BB_GS_NG(__half, false, 4) } }
   else { if (il) { BB_GS_NG(__nv_bfloat16, true, 8) } else { BB_GS_NG(__nv_bfloat16, false, 12) } }
 #undef BB_GS_NG
 #undef BB_GS_GO

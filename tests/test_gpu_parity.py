@@ -287,6 +287,62 @@ def test_generic_kernel_parity(kw):
     H.assert_fp_close(got, ref, "generic")
 
 
+# 16-entry table formats (NF4 / "fp4") on the fast kernels: PRMT table decode in the decode GEMV (m = 1) and in the tcgen05 dequant
+# warps (m > 1); reference semantics matmul_dequantize_impl.py:424-430 (nf: LUT[w]) and quantization.py:141-156 (fp4), support
+# matrix README.md:61-88.  Same oracle, same tolerance as every other float case.
+TABLE_CASES = [
+    dict(M=1, N=256, K=2048, W_dtype="nf4", group_size=128, with_scaling=True),
+    dict(M=1, N=4096, K=4096, W_dtype="nf4", group_size=128, with_scaling=True),
+    dict(M=1, N=512, K=1024, W_dtype="nf4", A_dtype="bfloat16", out_dtype="bfloat16", accum_dtype="float32", group_size=128, with_scaling=True),
+    dict(M=1, N=256, K=2048, W_dtype="fp4_e2m1", group_size=-1, with_scaling=True),
+    dict(M=1, N=256, K=1024, W_dtype="fp4_e2m1"),
+    dict(M=16, N=256, K=2048, W_dtype="nf4", group_size=128, with_scaling=True, with_bias=True),
+    dict(M=64, N=128, K=8192, W_dtype="fp4_e2m1", group_size=128, with_scaling=True),        # split-K
+    dict(M=300, N=256, K=2048, W_dtype="nf4", group_size=64, with_scaling=True),
+    dict(M=128, N=256, K=1024, W_dtype="nf4", A_dtype="bfloat16", out_dtype="bfloat16", accum_dtype="float32", group_size=128, with_scaling=True),
+    dict(M=200, N=384, K=1024, W_dtype="fp4_e2m1", A_dtype="bfloat16", out_dtype="bfloat16", accum_dtype="float32"),
+]
+
+
+@pytest.mark.parametrize("kw", TABLE_CASES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_table_formats_fast_kernels(kw):
+    kw = dict(kw)
+    M = kw["M"]
+    case = H.make_case(kw.pop("M"), kw.pop("N"), kw.pop("K"), **kw)
+    bf = kw.get("A_dtype") == "bfloat16"
+    op, got, ref = _run(case, "gemv_slab" if M == 1 else "gemm_ts_tcgen05")
+    H.assert_fp_close(got, ref, f"table format {kw['W_dtype']} M={M}", max_mismatched_ratio=2e-3 if bf else 0.0)
+    # and the generic kernel on the same inputs (the spec-order implementation these formats used before)
+    from bitblas_b200 import _lib
+    op2, got2, _ = _run(case, "generic_simt", force=_lib.BB_KERNEL_GENERIC)
+    H.assert_fp_close(got, got2, "fast vs generic", max_mismatched_ratio=2e-3 if bf else 0.0)
+
+
+@pytest.mark.parametrize("wd", ["e4m3_float8", "e5m2_float8"])
+@pytest.mark.parametrize("M,N,K,adt", [(1, 256, 1024, "float16"), (16, 256, 2048, "float16"), (300, 384, 1024, "float16"),
+                                       (64, 128, 8192, "float16"), (128, 256, 1024, "bfloat16")])
+def test_fp8_weights_tcgen05(wd, M, N, K, adt):
+    """8-bit float weights x 16-bit activations on the tcgen05 kernel (README.md:61-88 support matrix; decode formulas
+    quantization.py:169-182).  e4m3 codes are kept to normal numbers like in the generic-kernel test: the reference's bit trick
+    maps the zero / subnormal codes to large garbage values, and sums of those overflow fp16."""
+    bf = adt == "bfloat16"
+    case = H.make_case(M, N, K, A_dtype=adt, W_dtype=wd, out_dtype=adt, accum_dtype="float32" if bf else "float16", seed=M + K)
+    f = case["fields"]
+    if wd == "e4m3_float8":
+        f = torch.where((f & 0x78) == 0, f | 0x08, f)
+        f = torch.where((f & 0x7F) == 0x7F, f & 0xF7, f)
+        f = torch.where((f & 0x78) >= 0x50, f & 0xCF, f)       # |w| < 8: keeps K-long sums inside fp16
+    else:
+        f = torch.where((f & 0x7C) == 0x7C, f & 0xBF, f)       # no inf / nan codes
+        f = torch.where((f & 0x7C) >= 0x48, f & 0xB7 | 0x20, f)  # moderate magnitudes
+    case["fields"] = f
+    op, got, ref = _run(case, "gemm_ts_tcgen05")
+    H.assert_fp_close(got, ref, f"{wd} M={M}", max_mismatched_ratio=2e-3 if bf else 0.0)
+    from bitblas_b200 import _lib
+    _, got2, _ = _run(case, "generic_simt", force=_lib.BB_KERNEL_GENERIC)
+    H.assert_fp_close(got, got2, "fast vs generic", max_mismatched_ratio=2e-3 if bf else 0.0)
+
+
 def test_fast_kernels_agree_with_generic_on_device():
     """on-device cross check: same inputs through the forced generic kernel and the auto-dispatched one."""
     from bitblas_b200 import _lib
