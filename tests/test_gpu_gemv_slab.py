@@ -166,3 +166,37 @@ def test_gemv_slab_graph_replay_and_errors():
             g.replay()
             s.synchronize()
             assert torch.equal(out.cpu(), got.reshape(1, -1)), "graph replay differs"
+
+
+def test_captured_step_matches_eager():
+    """bitblas_b200.CapturedStep: pinned H2D + two dependent-free projections + pinned D2H replayed as one CUDA graph give the
+    eager results bit for bit, for fresh host inputs on every replay."""
+    import bitblas_b200 as bitblas
+    dev = torch.device("cuda")
+    shapes = [(512, 1024), (256, 2048)]
+    ops = []
+    for i, (N, K) in enumerate(shapes):
+        case = H.make_case(1, N, K, W_dtype="uint4", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized", seed=40 + i)
+        op = H.product_operator(case)
+        ops.append((op, H.product_weight(op, case, dev), case["scale"].to(dev), case["zeros"].to(dev), N, K))
+    Ks, Ns = [K for _, K in shapes], [N for N, _ in shapes]
+    hostA = torch.empty((sum(Ks),), dtype=torch.float16).pin_memory()
+    hostC = torch.empty((sum(Ns),), dtype=torch.float16).pin_memory()
+    devA = torch.empty((sum(Ks),), dtype=torch.float16, device=dev)
+    devC = torch.empty((sum(Ns),), dtype=torch.float16, device=dev)
+    av = [devA[:Ks[0]].view(1, -1), devA[Ks[0]:].view(1, -1)]
+    cv = [devC[:Ns[0]].view(1, -1), devC[Ns[0]:].view(1, -1)]
+
+    def fn():
+        for (op, W, s, z, N, K), a, c in zip(ops, av, cv):
+            op.forward(a, W, scale=s, zeros=z, output=c)
+
+    step = bitblas.CapturedStep(fn, h2d=[(devA, hostA)], d2h=[(hostC, devC)])
+    for trial in range(3):
+        hostA.copy_((torch.rand(sum(Ks), generator=torch.Generator().manual_seed(trial)) - 0.5).half())
+        step()
+        got = hostC.clone()
+        devA.copy_(hostA); fn(); torch.cuda.synchronize()
+        assert torch.equal(got, devC.cpu()), f"replay {trial}"
+    with pytest.raises(ValueError):
+        bitblas.CapturedStep(fn, h2d=[(devA, torch.empty(8))])       # unpinned host buffer
