@@ -512,44 +512,56 @@ gemv_slab_kernel(const __grid_constant__ CUtensorMap tmW, const SlabParams p) {
         }
       }
       __syncwarp();
+      auto decode_pair = [&](uint32_t xw, uint32_t yw, uint32_t (&ha)[4], uint32_t (&hb)[4]) {
+        if constexpr (FMT == 1) {
+          lut4_decode8(xw, lut4, ha);      // natural pairs (e0,e1) .. (e6,e7): the activation registers pair up as stored
+          lut4_decode8(yw, lut4, hb);
+        } else if constexpr (HI) {
+          const uint32_t xa = xw, ya = xw >> 8, xb = yw, yb = yw >> 8;
+          ha[0] = lop3_and_or(xa, 0x000f000fu, MAGIC); ha[1] = lop3_and_or(xa, 0x00f000f0u, MAGIC_HI);
+          ha[2] = lop3_and_or(ya, 0x000f000fu, MAGIC); ha[3] = lop3_and_or(ya, 0x00f000f0u, MAGIC_HI);
+          hb[0] = lop3_and_or(xb, 0x000f000fu, MAGIC); hb[1] = lop3_and_or(xb, 0x00f000f0u, MAGIC_HI);
+          hb[2] = lop3_and_or(yb, 0x000f000fu, MAGIC); hb[3] = lop3_and_or(yb, 0x00f000f0u, MAGIC_HI);
+        } else {
+          decode_u4x8_raw<T>(xw, ha);
+          decode_u4x8_raw<T>(yw, hb);
+        }
+      };
+      auto word_of = [&](int idx, int wi) -> uint32_t {
+        return wi == 0 ? wv[idx].x : (wi == 1 ? wv[idx].y : (wi == 2 ? wv[idx].z : wv[idx].w));
+      };
+      auto mma_pair = [&](float (&c)[4], const uint32_t (&ha)[4], const uint32_t (&hb)[4], int wi) {
 #pragma unroll
-      for (int pr = 0; pr < 4; ++pr) {
-        // fragment rows r <- weight row 16 tl + 4 ph + li, rows r + 8 <- that row + 8
-        const int tl = pr >> 1, ph = pr & 1;
-        const uint32_t wa[4] = {wv[4 * tl + ph].x, wv[4 * tl + ph].y, wv[4 * tl + ph].z, wv[4 * tl + ph].w};
-        const uint32_t wb[4] = {wv[4 * tl + ph + 2].x, wv[4 * tl + ph + 2].y, wv[4 * tl + ph + 2].z, wv[4 * tl + ph + 2].w};
+        for (int jj = 0; jj < 2; ++jj) {
+          const uint32_t af[4] = {ha[2 * jj], hb[2 * jj], ha[2 * jj + 1], hb[2 * jj + 1]};
+          uint32_t b0, b1;
+          if constexpr (IL || FMT == 1) {
+            b0 = Rv[wi][2 * jj]; b1 = Rv[wi][2 * jj + 1];
+          } else {
+            b0 = __byte_perm(Rv[wi][jj], Rv[wi][jj + 2], 0x5410);
+            b1 = __byte_perm(Rv[wi][jj], Rv[wi][jj + 2], 0x7632);
+          }
+          gs_mma<T>(c, af, b0, b1);
+        }
+      };
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr)
 #pragma unroll
         for (int j = 0; j < 4; ++j) cc[pr][j] = 0.f;
+      // fragment rows r <- weight row 16 tl + 4 ph + li, rows r + 8 <- that row + 8   (pr = 2 tl + ph)
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        const int ia = 4 * (pr >> 1) + (pr & 1);
 #pragma unroll
         for (int wi = 0; wi < 4; ++wi) {
           uint32_t ha[4], hb[4];
-          if constexpr (FMT == 1) {
-            lut4_decode8(wa[wi], lut4, ha);      // natural pairs (e0,e1) .. (e6,e7): the activation registers pair up as stored
-            lut4_decode8(wb[wi], lut4, hb);
-          } else if constexpr (HI) {
-            const uint32_t xa = wa[wi], ya = wa[wi] >> 8, xb = wb[wi], yb = wb[wi] >> 8;
-            ha[0] = lop3_and_or(xa, 0x000f000fu, MAGIC); ha[1] = lop3_and_or(xa, 0x00f000f0u, MAGIC_HI);
-            ha[2] = lop3_and_or(ya, 0x000f000fu, MAGIC); ha[3] = lop3_and_or(ya, 0x00f000f0u, MAGIC_HI);
-            hb[0] = lop3_and_or(xb, 0x000f000fu, MAGIC); hb[1] = lop3_and_or(xb, 0x00f000f0u, MAGIC_HI);
-            hb[2] = lop3_and_or(yb, 0x000f000fu, MAGIC); hb[3] = lop3_and_or(yb, 0x00f000f0u, MAGIC_HI);
-          } else {
-            decode_u4x8_raw<T>(wa[wi], ha);
-            decode_u4x8_raw<T>(wb[wi], hb);
-          }
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const uint32_t af[4] = {ha[2 * jj], hb[2 * jj], ha[2 * jj + 1], hb[2 * jj + 1]};
-            uint32_t b0, b1;
-            if constexpr (IL || FMT == 1) {
-              b0 = Rv[wi][2 * jj]; b1 = Rv[wi][2 * jj + 1];
-            } else {
-              b0 = __byte_perm(Rv[wi][jj], Rv[wi][jj + 2], 0x5410);
-              b1 = __byte_perm(Rv[wi][jj], Rv[wi][jj + 2], 0x7632);
-            }
-            gs_mma<T>(cc[pr], af, b0, b1);
-          }
+          decode_pair(word_of(ia, wi), word_of(ia + 2, wi), ha, hb);
+          mma_pair(cc[pr], ha, hb, wi);
         }
       }
+      // (measured and rejected, same box, profiles/r2_slab_v8_ab.txt: issuing the MMAs word-major -- consecutive MMAs to the four
+      //  independent accumulators -- 18.2 vs 17.1 us; folding both corrections into one per-row number in the finisher, which
+      //  removes 13 of the consumer's 334 instructions per unit but makes the finisher's output depend on its own sums, 17.3 vs 17.1 us)
     }
     // the group parameters and activation sums are needed only now: the finisher works on THIS unit while we decode it, so its
     // latency is off the critical path (with everything behind one barrier the consumers waited ~half the time although the
@@ -700,9 +712,9 @@ int gs_occupancy(KernelT k, int variant, int threads, int smem, int dev) {
   // per (kernel variant, device): opt-in shared memory once (the device maximum); per dynamic size: occupancy, cached
   struct Entry { int smem, occ; };
   static std::mutex mu;
-  static Entry cache[24][GS_MAX_DEVICES][8];
-  static int used[24][GS_MAX_DEVICES];
-  static bool attr[24][GS_MAX_DEVICES];
+  static Entry cache[32][GS_MAX_DEVICES][8];
+  static int used[32][GS_MAX_DEVICES];
+  static bool attr[32][GS_MAX_DEVICES];
   static bool init = false;
   std::lock_guard<std::mutex> lk(mu);
   if (!init) { memset(cache, 0, sizeof(cache)); memset(used, 0, sizeof(used)); memset(attr, 0, sizeof(attr)); init = true; }

@@ -1,9 +1,24 @@
 #!/bin/bash
-# GPU session: the whole -m gpu suite, then the bench (N = 1) with its launch list
+# Final GPU session of a round: the whole -m gpu suite, the bench (N = 1) + reference arm, the ncu launch list of the bench command,
+# full-set captures of the two dominant kernels, and a compute-sanitizer pass over a subset of the parity tests.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu --durations=12 2>&1 | tail -40 > gpurun_out/r2_pytest_gpu.txt
-tail -5 gpurun_out/r2_pytest_gpu.txt
+timeout 1500 python -m pytest tests -q -m gpu --durations=8 2>&1 | tail -30 > gpurun_out/r2_pytest_gpu.txt
+tail -3 gpurun_out/r2_pytest_gpu.txt
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
-tail -c 3000 gpurun_out/r2_bench.json; tail -5 gpurun_out/r2_bench.err
+tail -c 1500 gpurun_out/r2_bench.json; tail -5 gpurun_out/r2_bench.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>> gpurun_out/r2_bench.err
-tail -c 600 gpurun_out/r2_bench_reference_arm.json
+tail -c 400 gpurun_out/r2_bench_reference_arm.json
+if [ "$1" != "quick" ]; then
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r2_launches.csv \
+  python bench.py --steps 2 --warmup 3 --skip-cpu --only x > gpurun_out/r2_launch_run.log 2>&1
+tail -2 gpurun_out/r2_launch_run.log
+timeout 600 ncu --set full --clock-control none -k regex:gemm_ts -s 4 -c 1 -o gpurun_out/r2_gemm_prof \
+  python bench.py --steps 2 --warmup 3 --skip-cpu --only gemm > gpurun_out/r2_gemm_ncu.log 2>&1
+tail -2 gpurun_out/r2_gemm_ncu.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemv_slab -s 12 -c 2 -o gpurun_out/r2_slab_prof \
+  tools/gemv_bench --iters 5 --nocheck 12288x12288 > gpurun_out/r2_slab_ncu.log 2>&1
+tail -2 gpurun_out/r2_slab_ncu.log
+{ echo "# compute-sanitizer memcheck"; timeout 500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_scatter.py tests/test_gpu_tile.py tests/test_gpu_gemv_slab.py -q -m gpu -x -k "scatter_matches or device_retile or (tiled_matches and 256) or (gemv_slab_parity and 256)" 2>&1 | tail -8;
+  echo "# compute-sanitizer racecheck"; timeout 400 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_scatter.py -q -m gpu -x -k "scatter_matches" 2>&1 | tail -6; } > gpurun_out/r2_sanitizer.txt
+cat gpurun_out/r2_sanitizer.txt
+fi
