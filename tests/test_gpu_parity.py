@@ -215,6 +215,13 @@ GEMM_CASES = [
     dict(M=96, N=256, K=1024, W_dtype="int4", fast_decoding=False, group_size=-1, with_scaling=True),
     dict(M=128, N=256, K=1024, W_dtype="uint4", A_dtype="bfloat16", out_dtype="bfloat16", group_size=128, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
     dict(M=128, N=128, K=512, W_dtype="uint2", A_dtype="bfloat16", out_dtype="bfloat16", group_size=128, with_scaling=True),
+    # group length (3 k-blocks) that the dequant groups' stride (4 for BM <= 128, 2 for BM = 256) neither divides nor is a multiple
+    # of: a warp's consecutive k-blocks then skip one or two groups, and the parameter prefetch must name the right one
+    # (round-1 advisor finding: kb = 12 consumed group 3's scale)
+    dict(M=16, N=128, K=1536, W_dtype="uint4", group_size=192, with_scaling=True, with_zeros=True, zeros_mode="quantized"),
+    dict(M=100, N=256, K=1536, W_dtype="uint4", group_size=192, with_scaling=True, with_zeros=True, zeros_mode="original"),
+    dict(M=300, N=256, K=3072, W_dtype="uint4", group_size=192, with_scaling=True, with_zeros=True, zeros_mode="rescale"),
+    dict(M=64, N=128, K=1920, W_dtype="uint2", group_size=320, with_scaling=True),
 ]
 
 
