@@ -951,6 +951,10 @@ int launch_ts_bm2(const MatmulArgs& a, const TsParams& p) {
   if (a.m <= 32) return launch_ts_inst<T, BITS, 32, IL>(a, p);
   if (a.m <= 64) return launch_ts_inst<T, BITS, 64, IL>(a, p);
   if (a.m <= 128) return launch_ts_inst<T, BITS, 128, IL>(a, p);
+  // tuning hook: BB_TS_BM=128 runs large m on the 128-column tile (two CTAs per SM: one CTA's epilogue overlaps the other's main loop,
+  // at twice the decode work per output)
+  static const int force_bm = [] { const char* e = getenv("BB_TS_BM"); return e ? atoi(e) : 0; }();
+  if (force_bm == 128) return launch_ts_inst<T, BITS, 128, IL>(a, p);
   return launch_ts_inst<T, BITS, 256, IL>(a, p);
 }
 template <typename T>
