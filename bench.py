@@ -305,8 +305,10 @@ def rotating_kernel_time(op, prm, A, out, reps=5, min_bytes=300 * 1024 * 1024):
         op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
     torch.cuda.synchronize()
 
+    npass = max(2 * ncopies, 40)     # launches per pass: the graph-launch latency of a pass (a few us) is spread over >= 40 kernels
+
     def one_pass():
-        for i in range(2 * ncopies):
+        for i in range(npass):
             c = copies[i % ncopies]
             op.forward(A, c["W"], scale=c["scale"], zeros=c["zeros"], output=out)
 
@@ -337,7 +339,7 @@ def rotating_kernel_time(op, prm, A, out, reps=5, min_bytes=300 * 1024 * 1024):
             one_pass()
         e.record()
         torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e) / (2 * ncopies))
+        ts.append(s.elapsed_time(e) / npass)
     return statistics.median(ts), ncopies, graph is not None
 
 
@@ -516,7 +518,7 @@ def main():
     # The step is captured once per parameter set in a CUDA graph (four launches with their programmatic-dependent-launch
     # edges + the device barrier) and replayed: at 8 GPUs a shard's kernel takes a few microseconds, the four Python calls that
     # launch them do not.  Same code path at every world size; BB_BENCH_STEP_GRAPH=0 (or a failed capture) issues the launches directly.
-    step_graphs, launches_per_step = None, None
+    step_graphs, launches_per_step, step_block = None, None, None
     if os.environ.get("BB_BENCH_STEP_GRAPH", "1") != "0":
         try:
             side = torch.cuda.Stream()
@@ -534,18 +536,26 @@ def main():
                         gemv_step_on(ops_c)
                     launches_per_step = lib.bb_launch_count() - l0
                     gs.append(gph)
+                # a block of consecutive steps in ONE graph (a decoder runs its layers' projections back to back: the launch-bound
+                # inner loop belongs in one graph); the remainder of --steps is replayed step by step
+                block_len = nsets * max(1, round(10 / nsets))
+                block = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(block, stream=side):
+                    for j in range(block_len):
+                        gemv_step_on(sets[j % nsets])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             step_graphs = gs
+            step_block = (block, block_len)
         except Exception as ex:  # noqa: BLE001
             print(f"[bench] step graph capture unavailable on rank {rank} ({ex}); issuing launches directly", file=sys.stderr)
-            step_graphs = None
+            step_graphs, step_block = None, None
             torch.cuda.synchronize()
     if world > 1:   # the choice must be collective: a rank replaying a graph and a rank launching directly still meet in the barrier, but keep it simple
         flag = torch.tensor([1 if step_graphs is not None else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
-            step_graphs = None
+            step_graphs, step_block = None, None
     step_no = [0]
 
     def gemv_step():
@@ -558,16 +568,37 @@ def main():
 
     if rank == 0:
         sampler.start()
-    for _ in range(warmup):
-        gemv_step()
+    def run_steps(k):
+        """exactly k steps: whole blocks (one graph launch per `block_len` steps), then the remainder one step per graph launch"""
+        if step_block is not None:
+            nb, rem = divmod(k, step_block[1])
+            for _ in range(nb):
+                step_block[0].replay()
+            step_no[0] = 0          # the remainder continues the parameter-set rotation where a block ends
+        else:
+            rem = k
+        for _ in range(rem):
+            gemv_step()
+
+    run_steps(warmup)
+    if step_block is not None:
+        step_block[0].replay()      # (the block graph itself, whatever --warmup is)
     torch.cuda.synchronize()
     launches0 = lib.bb_launch_count()
-    ms_step = timed(gemv_step, args.steps, 0, barrier)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run_steps(args.steps)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
     # kernels of this library launched inside the timed region (replayed graph launches are not seen by the library's counter)
     launches = (launches_per_step * args.steps) if step_graphs is not None else (lib.bb_launch_count() - launches0)
     ms_step = max_over_ranks(ms_step)
     value = total_bytes / (ms_step * 1e-3) / 1e9
-    result["step_method"] = {"cuda_graph": step_graphs is not None, "parameter_sets": nsets,
+    result["step_method"] = {"cuda_graph": step_graphs is not None, "steps_per_graph_launch": step_block[1] if step_block else 1,
+                             "parameter_sets": nsets,
                              "per_gpu_bytes_per_step": per_gpu}
 
     # per-shape kernel time, cold L2 (rotating parameter copies)
