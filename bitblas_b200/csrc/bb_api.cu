@@ -65,6 +65,10 @@ static int validate(const bb_matmul_desc* d) {
   }
   if (d->reserved[0] || d->reserved[1]) { set_error("reserved fields must be zero"); return 1; }
   if (d->w_tile != BB_TILE_ROW_MAJOR && d->w_tile != BB_TILE_SLAB) { set_error("bad w_tile %d", d->w_tile); return 1; }
+  if (d->w_tile == BB_TILE_SLAB && !((d->w_fmt == BB_W_UINT || d->w_fmt == BB_W_INT) && (d->w_bits == 4 || d->w_bits == 2))) {
+    set_error("BB_TILE_SLAB is defined for 4- and 2-bit integer weights (the combinations the parity suite covers)");
+    return 1;
+  }
   if (d->w_tile == BB_TILE_SLAB && !tile_shape_ok(*d)) {
     set_error("BB_TILE_SLAB needs N %% %d == 0 and K*bits/8 %% %d == 0 (N=%d K=%d bits=%d)", BB_TILE_ROWS, BB_TILE_ROW_BYTES, d->N, d->K, d->w_bits);
     return 1;
